@@ -1,0 +1,168 @@
+/*
+ * qcut_b200.h -- C ABI of the B200-native reconstruction hot path.
+ *
+ * This is the drop-in boundary for qiskit-addon-cutting's
+ *     reconstruct_expectation_values(results, coefficients, observables)
+ * (reference: qiskit_addon_cutting/cutting_reconstruction.py:31-170).  The reference is pure
+ * Python and has no FFI of its own; the entry points below are what a ctypes binding for that
+ * function binds (see INTEGRATION.md for the reference-side stub).  Plain pointers and sizes
+ * only -- no torch / numpy / Qiskit types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative qcut_status on failure; the message
+ *     of the last failure on the calling thread is available from qcut_last_error();
+ *   - "d_" pointers are device (HBM) pointers owned by the caller, "h_" pointers are host
+ *     pointers; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all launches are asynchronous on `stream`; nothing here synchronises unless stated.
+ *
+ * Data layout
+ *   - shot data: one byte buffer.  Each PUB (one subexperiment result) owns two row-major
+ *     byte matrices, observable_measurements (shots x nb_obs) and qpd_measurements
+ *     (shots x nb_qpd), exactly the bytes of Qiskit's BitArray.array: big-endian within a
+ *     row (reference cutting_reconstruction.py:152-158).  Matrices start at 16-byte aligned
+ *     offsets.
+ *   - masks: per group, n_terms x nb_obs bytes, big-endian rows (same memory order as the
+ *     shot rows, so kernels AND raw bytes; reference utils/observable_grouping.py:140-151).
+ *   - tallies: int64, tally[pub.tally_offset + t] = sum over shots of
+ *     (-1)^(popcount(qpd row) + popcount(obs row AND mask_t))
+ *     (reference cutting_reconstruction.py:213-220, summed exactly instead of in fp64).
+ */
+#ifndef QCUT_B200_H
+#define QCUT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCUT_ABI_VERSION 1
+/* Shots per scheduling tile: tile_start[] handed to qcut_tally_launch counts tiles of this size. */
+#define QCUT_TILE_SHOTS 4096
+/* Widest observable row (bytes) the kernels accept: 64 bytes = 512 measured qubits per group. */
+#define QCUT_MAX_OBS_BYTES 64
+
+typedef enum qcut_status {
+  QCUT_OK = 0,
+  QCUT_ERR_INVALID = -1,     /* bad argument (null pointer, size, unsupported width) */
+  QCUT_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  QCUT_ERR_JIT = -3,         /* NVRTC specialisation failed */
+  QCUT_ERR_NOMEM = -4
+} qcut_status;
+
+/* One commuting observable group as measured by the PUBs that reference it
+ * (reference: CommutingObservableGroup, utils/observable_grouping.py:116-157). */
+typedef struct qcut_group_desc {
+  uint32_t n_terms;     /* T: number of Pauli terms (masks) in the group                    */
+  uint32_t nb_obs;      /* bytes per observable_measurements row                            */
+  uint32_t mask_offset; /* byte offset of the T x nb_obs mask rows inside the mask buffer    */
+  uint32_t reserved;
+} qcut_group_desc;
+
+/* One PUB = the result of one subexperiment: result[i * G + g] in the reference's indexing
+ * (reference cutting_reconstruction.py:142,152-155). */
+typedef struct qcut_pub_desc {
+  uint64_t obs_offset;   /* byte offset of observable_measurements rows in the data buffer  */
+  uint64_t qpd_offset;   /* byte offset of qpd_measurements rows                            */
+  uint64_t tally_offset; /* index (int64 units) of this PUB's first tally                   */
+  uint32_t shots;        /* rows in both matrices (qpd_array.shape[0], reference :155)      */
+  uint32_t group;        /* index into the plan's group table                               */
+  uint32_t nb_qpd;       /* bytes per qpd_measurements row                                  */
+  uint32_t reserved;
+} qcut_pub_desc;
+
+/* One (group, term) slot of the observable lookup (reference utils/observable_grouping.py:220-224). */
+typedef struct qcut_slot {
+  uint32_t group; /* group index *within the subsystem* (0 .. G_label-1) */
+  uint32_t term;  /* term index within that group                        */
+} qcut_slot;
+
+/* One subsystem ("partition label") as seen by the reduction kernel. */
+typedef struct qcut_label_desc {
+  uint64_t pub_base;     /* index of the label's first PUB in the pub table (local to this rank)   */
+  uint32_t num_groups;   /* G_label: PUB of (coefficient i, group g) is pub_base + i * G_label + g */
+  uint32_t lookup_base;  /* index into lookup_start[] of this label's first observable            */
+} qcut_label_desc;
+
+typedef struct qcut_plan qcut_plan;
+
+int qcut_abi_version(void);
+const char* qcut_last_error(void);
+
+/* Number of visible CUDA devices (0 if none / no driver).  Never fails. */
+int qcut_device_count(void);
+
+/* ---- plan: group table + masks resident in HBM, plus kernels specialised for them -------------
+ * Replaces the per-call host state the reference builds at cutting_reconstruction.py:113-116.
+ * flags: bit 0 = disable NVRTC specialisation (always use the generic kernel). */
+#define QCUT_PLAN_NO_JIT 1u
+int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
+                     size_t mask_bytes, unsigned flags, qcut_plan** out_plan);
+void qcut_plan_destroy(qcut_plan* plan);
+/* 0 = generic kernel, 1 = bit-sliced specialised kernel; <0 on error. */
+int qcut_plan_group_kernel(const qcut_plan* plan, int group);
+/* Copies the generated CUDA source of the specialised kernels (NUL terminated) into buf;
+ * returns the full length needed.  For inspection (nvcc -Xptxas -v, cuobjdump) only. */
+size_t qcut_plan_source(const qcut_plan* plan, char* buf, size_t buf_len);
+
+/* ---- K1: parity tallies (reference cutting_reconstruction.py:152-161 + :196-222) -------------
+ * Work is scheduled in tiles of QCUT_TILE_SHOTS consecutive shots of one PUB:
+ *   d_tile_start[p] = number of tiles in PUBs 0..p-1 (n_pubs + 1 entries, last == n_tiles),
+ *   d_tile_pub[t]   = PUB that owns tile t (n_tiles entries).
+ * Zeroes d_tallies[0 .. n_tallies) and accumulates into it. */
+int qcut_tally_launch(const qcut_plan* plan, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
+                      int64_t n_pubs, const int64_t* d_tile_start, const uint32_t* d_tile_pub,
+                      int64_t n_tiles, int64_t* d_tallies, int64_t n_tallies, void* stream);
+
+/* ---- K2: coefficient-weighted product over subsystems, summed over subexperiment tuples -------
+ * (reference cutting_reconstruction.py:134-136,163-168):
+ *   out[k] = sum_i coeff[i] * prod_label mean_{(g,t) in lookup(label,k)} tally / shots
+ * with the expectation of PUB (label, i, g) taken as tally/shots (one correctly rounded fp64
+ * division).  Deterministic: fixed partition of i, fixed-order combination.  d_workspace must
+ * hold qcut_reduce_workspace_bytes(n_coeffs, n_obs) bytes. */
+size_t qcut_reduce_workspace_bytes(int64_t n_coeffs, int n_obs);
+int qcut_reduce_launch(const int64_t* d_tallies, const qcut_pub_desc* d_pubs,
+                       const qcut_label_desc* d_labels, int n_labels,
+                       const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
+                       const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
+                       void* d_workspace, void* stream);
+
+/* ---- SamplerV1 quasi-distributions (reference cutting_reconstruction.py:143-149,173-193) -------
+ * For PUB p, outcomes [d_dist_start[p], d_dist_start[p+1]) hold (obs bits, qpd bits, weight):
+ *   d_expvals[pub.tally_offset + t] = sum_o weight_o * sign_o(t),
+ * accumulated sequentially in the order given, i.e. bit-identical to the reference's dict-order
+ * loop.  obs/qpd bit strings and masks are little-endian uint64 limbs (n_limbs_obs / n_limbs_qpd
+ * per outcome, n_limbs_obs per mask); d_groups[g].mask_offset indexes d_mask_limbs in limbs and
+ * nb_obs is ignored.  Only pub.group and pub.tally_offset of d_pubs are read. */
+int qcut_quasi_launch(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_group_desc* d_groups,
+                      const uint64_t* d_mask_limbs, const int64_t* d_dist_start,
+                      const uint64_t* d_obs_bits, int n_limbs_obs, const uint64_t* d_qpd_bits,
+                      int n_limbs_qpd, const double* d_weights, double* d_expvals, void* stream);
+/* K2 on fp64 per-PUB expectation values instead of tallies (V1 path). */
+int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_pubs,
+                               const qcut_label_desc* d_labels, int n_labels,
+                               const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
+                               const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
+                               void* d_workspace, void* stream);
+
+/* ---- host staging: gather many borrowed BitArray buffers into one pinned buffer ---------------
+ * Copies n_arrays host buffers (h_src[i], h_bytes[i] bytes) to h_dst + h_dst_offset[i] with
+ * n_threads worker threads (0 = hardware concurrency).  Pure host code; used on the end-to-end
+ * path so that one large H2D copy replaces 2 * n_pubs small ones. */
+int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,
+                     int64_t n_arrays, void* h_dst, int n_threads);
+
+/* ---- host-only helpers (no GPU needed): inspection and CPU-side testing of the specialisation -----
+ * qcut_generate_source: the CUDA translation unit qcut_plan_create would hand to NVRTC for these
+ * groups; h_group_variant[g] receives the specialised-kernel variant of group g or -1 (generic
+ * kernel).  Returns the length needed including the NUL, 0 on bad input or nothing to specialise.
+ * qcut_compile_source: NVRTC -> sm_100a cubin (size, and the image if cubin_buf is large enough). */
+size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
+                            size_t mask_bytes, int* h_group_variant, char* buf, size_t buf_len);
+int qcut_compile_source(const char* source, size_t* cubin_bytes, char* cubin_buf, size_t cubin_buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QCUT_B200_H */

@@ -1,0 +1,250 @@
+// extern "C" entry points of libqcut_b200.so (see include/qcut_b200.h).
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <new>
+#include <thread>
+
+#include "common.cuh"
+
+namespace qcut {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t err, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorName(err) + " (" + cudaGetErrorString(err) + ")";
+  return QCUT_ERR_CUDA;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+// defined in tally_generic.cu / reduce.cu / jit.cu
+int launch_tally_generic(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, const uint32_t*,
+                         const int64_t*, int64_t, int64_t*, cudaStream_t);
+int launch_tally_sliced(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, const uint32_t*,
+                        const int64_t*, int64_t, int64_t*, cudaStream_t);
+int jit_specialise(qcut_plan* plan);
+void jit_release(qcut_plan* plan);
+template <typename TallyT>
+int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, int, const uint32_t*,
+                  const qcut_slot*, const double*, int64_t, int, double*, void*, cudaStream_t);
+size_t reduce_workspace_bytes(int64_t, int);
+int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const uint64_t*, const int64_t*,
+                 const uint64_t*, int, const uint64_t*, int, const double*, double*, cudaStream_t);
+
+}  // namespace qcut
+
+using namespace qcut;
+
+extern "C" {
+
+int qcut_abi_version(void) { return QCUT_ABI_VERSION; }
+
+const char* qcut_last_error(void) { return g_last_error.c_str(); }
+
+int qcut_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
+                     size_t mask_bytes, unsigned flags, qcut_plan** out_plan) {
+  if (!out_plan) return set_error("qcut_plan_create: out_plan is NULL"), QCUT_ERR_INVALID;
+  *out_plan = nullptr;
+  if (n_groups <= 0 || !h_groups) return set_error("qcut_plan_create: no groups"), QCUT_ERR_INVALID;
+  qcut_plan* plan = new (std::nothrow) qcut_plan();
+  if (!plan) return set_error("qcut_plan_create: out of host memory"), QCUT_ERR_NOMEM;
+  plan->n_groups = n_groups;
+  plan->flags = flags;
+  plan->groups.assign(h_groups, h_groups + n_groups);
+  if (mask_bytes) plan->masks.assign(h_masks, h_masks + mask_bytes);
+
+  // Mask rows -> zero padded little-endian words in memory order (what the kernels AND with).
+  std::vector<uint32_t> words;
+  plan->groups_dev.resize(n_groups);
+  for (int g = 0; g < n_groups; ++g) {
+    const qcut_group_desc& gd = h_groups[g];
+    if (gd.nb_obs == 0 || gd.nb_obs > QCUT_MAX_OBS_BYTES) {
+      set_error("qcut_plan_create: group " + std::to_string(g) + " has an unsupported observable row width of " +
+                std::to_string(gd.nb_obs) + " bytes (1.." + std::to_string(QCUT_MAX_OBS_BYTES) + " supported)");
+      delete plan;
+      return QCUT_ERR_INVALID;
+    }
+    if ((size_t)gd.mask_offset + (size_t)gd.n_terms * gd.nb_obs > mask_bytes) {
+      set_error("qcut_plan_create: group " + std::to_string(g) + " masks run past the mask buffer");
+      delete plan;
+      return QCUT_ERR_INVALID;
+    }
+    GroupDev& dev = plan->groups_dev[g];
+    dev = GroupDev{};
+    dev.n_terms = gd.n_terms;
+    dev.nb_obs = gd.nb_obs;
+    dev.n_words = (gd.nb_obs + 3) / 4;
+    dev.word_offset = (uint32_t)words.size();
+    dev.kernel = KERNEL_GENERIC;
+    for (uint32_t t = 0; t < gd.n_terms; ++t) {
+      const uint8_t* row = h_masks + gd.mask_offset + (size_t)t * gd.nb_obs;
+      for (uint32_t w = 0; w < dev.n_words; ++w) {
+        uint32_t v = 0;
+        for (uint32_t j = 0; j < 4 && 4 * w + j < gd.nb_obs; ++j) v |= (uint32_t)row[4 * w + j] << (8 * j);
+        words.push_back(v);
+      }
+    }
+  }
+
+  if (!(flags & QCUT_PLAN_NO_JIT)) {
+    const int rc = jit_specialise(plan);  // marks groups_dev[g].kernel / variant, builds the module
+    if (rc != QCUT_OK) {
+      delete plan;
+      return rc;
+    }
+  }
+  for (const GroupDev& dev : plan->groups_dev) {
+    plan->any_generic |= dev.kernel == KERNEL_GENERIC;
+    plan->any_sliced |= dev.kernel == KERNEL_SLICED;
+  }
+
+  auto fail = [&](cudaError_t err, const char* what) {
+    const int rc = cuda_fail(err, what);
+    qcut_plan_destroy(plan);
+    return rc;
+  };
+  cudaError_t err = cudaMalloc(&plan->d_groups, sizeof(GroupDev) * n_groups);
+  if (err != cudaSuccess) return fail(err, "cudaMalloc(groups)");
+  err = cudaMemcpy(plan->d_groups, plan->groups_dev.data(), sizeof(GroupDev) * n_groups, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return fail(err, "cudaMemcpy(groups)");
+  const size_t wbytes = std::max<size_t>(words.size(), 1) * sizeof(uint32_t);
+  err = cudaMalloc(&plan->d_mask_words, wbytes);
+  if (err != cudaSuccess) return fail(err, "cudaMalloc(mask words)");
+  if (!words.empty()) {
+    err = cudaMemcpy(plan->d_mask_words, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) return fail(err, "cudaMemcpy(mask words)");
+  }
+  *out_plan = plan;
+  return QCUT_OK;
+}
+
+void qcut_plan_destroy(qcut_plan* plan) {
+  if (!plan) return;
+  jit_release(plan);
+  if (plan->d_groups) cudaFree(plan->d_groups);
+  if (plan->d_mask_words) cudaFree(plan->d_mask_words);
+  delete plan;
+}
+
+int qcut_plan_group_kernel(const qcut_plan* plan, int group) {
+  if (!plan || group < 0 || group >= plan->n_groups) return set_error("qcut_plan_group_kernel: bad group"), QCUT_ERR_INVALID;
+  return (int)plan->groups_dev[group].kernel;
+}
+
+size_t qcut_plan_source(const qcut_plan* plan, char* buf, size_t buf_len) {
+  if (!plan) return 0;
+  const size_t need = plan->jit_source.size() + 1;
+  if (buf && buf_len) {
+    const size_t n = std::min(buf_len - 1, plan->jit_source.size());
+    std::memcpy(buf, plan->jit_source.data(), n);
+    buf[n] = '\0';
+  }
+  return need;
+}
+
+int qcut_tally_launch(const qcut_plan* plan, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
+                      int64_t n_pubs, const int64_t* d_tile_start, const uint32_t* d_tile_pub,
+                      int64_t n_tiles, int64_t* d_tallies, int64_t n_tallies, void* stream) {
+  if (!plan) return set_error("qcut_tally_launch: plan is NULL"), QCUT_ERR_INVALID;
+  if (n_pubs < 0 || n_tiles < 0 || n_tallies < 0) return set_error("qcut_tally_launch: negative size"), QCUT_ERR_INVALID;
+  if (n_tallies > 0 && !d_tallies) return set_error("qcut_tally_launch: d_tallies is NULL"), QCUT_ERR_INVALID;
+  if (n_tiles > 0 && (!d_data || !d_pubs || !d_tile_start || !d_tile_pub)) return set_error("qcut_tally_launch: NULL input"), QCUT_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_tallies > 0) QCUT_CUDA(cudaMemsetAsync(d_tallies, 0, sizeof(int64_t) * (size_t)n_tallies, s));
+  if (n_pubs == 0 || n_tiles == 0) return QCUT_OK;
+  if (plan->any_sliced) {
+    const int rc = launch_tally_sliced(plan, d_data, d_pubs, d_tile_pub, d_tile_start, n_tiles, d_tallies, s);
+    if (rc != QCUT_OK) return rc;
+  }
+  if (plan->any_generic) {
+    const int rc = launch_tally_generic(plan, d_data, d_pubs, d_tile_pub, d_tile_start, n_tiles, d_tallies, s);
+    if (rc != QCUT_OK) return rc;
+  }
+  return QCUT_OK;
+}
+
+size_t qcut_reduce_workspace_bytes(int64_t n_coeffs, int n_obs) { return reduce_workspace_bytes(n_coeffs, n_obs); }
+
+int qcut_reduce_launch(const int64_t* d_tallies, const qcut_pub_desc* d_pubs, const qcut_label_desc* d_labels,
+                       int n_labels, const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
+                       const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
+                       void* d_workspace, void* stream) {
+  if (!d_out || !d_workspace || n_labels < 0 || n_coeffs < 0)
+    return set_error("qcut_reduce_launch: bad argument"), QCUT_ERR_INVALID;
+  return launch_reduce<int64_t>(d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs,
+                                n_coeffs, n_obs, d_out, d_workspace, static_cast<cudaStream_t>(stream));
+}
+
+int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_pubs,
+                               const qcut_label_desc* d_labels, int n_labels, const uint32_t* d_lookup_start,
+                               const qcut_slot* d_lookup, const double* d_coeffs, int64_t n_coeffs, int n_obs,
+                               double* d_out, void* d_workspace, void* stream) {
+  if (!d_out || !d_workspace || n_labels < 0 || n_coeffs < 0)
+    return set_error("qcut_reduce_expvals_launch: bad argument"), QCUT_ERR_INVALID;
+  return launch_reduce<double>(d_expvals, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs,
+                               n_coeffs, n_obs, d_out, d_workspace, static_cast<cudaStream_t>(stream));
+}
+
+int qcut_quasi_launch(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_group_desc* d_groups,
+                      const uint64_t* d_mask_limbs, const int64_t* d_dist_start, const uint64_t* d_obs_bits,
+                      int n_limbs_obs, const uint64_t* d_qpd_bits, int n_limbs_qpd, const double* d_weights,
+                      double* d_expvals, void* stream) {
+  if (n_pubs < 0 || n_limbs_obs < 0 || n_limbs_qpd < 0) return set_error("qcut_quasi_launch: bad size"), QCUT_ERR_INVALID;
+  return launch_quasi(d_pubs, n_pubs, d_groups, d_mask_limbs, d_dist_start, d_obs_bits, n_limbs_obs,
+                      d_qpd_bits, n_limbs_qpd, d_weights, d_expvals, static_cast<cudaStream_t>(stream));
+}
+
+int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,
+                     int64_t n_arrays, void* h_dst, int n_threads) {
+  if (n_arrays < 0 || (n_arrays > 0 && (!h_src || !h_bytes || !h_dst_offset || !h_dst)))
+    return set_error("qcut_gather_host: bad argument"), QCUT_ERR_INVALID;
+  if (n_arrays == 0) return QCUT_OK;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<int64_t>(n_threads, n_arrays);
+  // Dynamic chunks of arrays so that ragged sizes balance across workers.
+  std::atomic<int64_t> next{0};
+  const int64_t chunk = std::max<int64_t>(1, n_arrays / (n_threads * 16));
+  auto worker = [&]() {
+    for (;;) {
+      const int64_t lo = next.fetch_add(chunk);
+      if (lo >= n_arrays) return;
+      const int64_t hi = std::min(n_arrays, lo + chunk);
+      for (int64_t i = lo; i < hi; ++i)
+        if (h_bytes[i]) std::memcpy(static_cast<char*>(h_dst) + h_dst_offset[i], h_src[i], h_bytes[i]);
+    }
+  };
+  if (n_threads == 1) {
+    worker();
+    return QCUT_OK;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(n_threads);
+  for (int i = 0; i < n_threads; ++i) pool.emplace_back(worker);
+  for (auto& th : pool) th.join();
+  return QCUT_OK;
+}
+
+}  // extern "C"

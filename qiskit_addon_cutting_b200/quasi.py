@@ -1,0 +1,112 @@
+"""SamplerV1 (quasi-distribution) results on the device.
+
+Reference: ``cutting_reconstruction.py:143-149`` with ``_process_outcome`` (``:173-193``) and
+``_outcome_to_int`` (``:225-232``).  Each outcome key is split on the host into its observable
+bits (low ``max(1, len(pauli_indices))`` bits) and qpd bits; the kernel accumulates
+``weight * sign`` per (PUB, term) sequentially in dict order, which reproduces the reference's
+fp64 result bit for bit; K2 then runs on those expectation values.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GROUP_DTYPE, LABEL_DTYPE, PUB_DTYPE, SLOT_DTYPE, check
+from .engine import _stream_ptr, _to_device
+
+
+def _outcome_to_int(outcome) -> int:
+    if isinstance(outcome, (int, np.integer)):
+        return int(outcome)
+    outcome = outcome.replace(" ", "")
+    if len(outcome) < 2 or outcome[1] in ("0", "1"):
+        return int(f"0b{outcome}", 0)
+    return int(outcome, 0)
+
+
+def _limbs(value: int, n: int) -> list[int]:
+    return [(value >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(n)]
+
+
+def reconstruct_v1(results: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int) -> torch.Tensor:
+    _lib.require_device()
+    lib = _lib.load()
+    # First pass: split outcomes, find limb counts.
+    pubs_raw = []  # (global group, [(obs, qpd, weight)])
+    group_rows, label_rows, lookup_start, lookup_rows = [], [], [0], []
+    mask_ints: list[list[int]] = []
+    max_obs_bits, max_qpd_bits = 1, 1
+    for li, (result, coll) in enumerate(zip(results, collections)):
+        n_groups = len(coll.groups)
+        label_rows.append((len(pubs_raw), n_groups, li * n_obs))
+        for slots in coll.lookup_indices:
+            lookup_rows.extend(slots)
+            lookup_start.append(len(lookup_rows))
+        g_base = len(mask_ints)
+        for cog in coll.groups:
+            mask_ints.append(list(cog.pauli_bitmasks))
+            max_obs_bits = max(max_obs_bits, cog.num_measured_bits)
+        for i in range(i_lo, i_hi):
+            for g, cog in enumerate(coll.groups):
+                nmb = cog.num_measured_bits
+                items = []
+                for outcome, weight in result.quasi_dists[i * n_groups + g].items():
+                    o = _outcome_to_int(outcome)
+                    obs, qpd = o & ((1 << nmb) - 1), o >> nmb
+                    max_qpd_bits = max(max_qpd_bits, qpd.bit_length())
+                    items.append((obs, qpd, float(weight)))
+                pubs_raw.append((g_base + g, items))
+    n_lo, n_lq = (max_obs_bits + 63) // 64, (max_qpd_bits + 63) // 64
+
+    mask_limbs, offset = [], 0
+    for masks in mask_ints:
+        group_rows.append((len(masks), 0, offset, 0))
+        for m in masks:
+            mask_limbs.extend(_limbs(m, n_lo))
+        offset += len(masks) * n_lo
+    pubs = np.zeros(len(pubs_raw), dtype=PUB_DTYPE)
+    dist_start = np.zeros(len(pubs_raw) + 1, dtype=np.int64)
+    obs_limbs, qpd_limbs, weights = [], [], []
+    tally_offset = 0
+    for p, (group, items) in enumerate(pubs_raw):
+        pubs[p]["group"] = group
+        pubs[p]["tally_offset"] = tally_offset
+        tally_offset += len(mask_ints[group])
+        for obs, qpd, w in items:
+            obs_limbs.extend(_limbs(obs, n_lo))
+            qpd_limbs.extend(_limbs(qpd, n_lq))
+            weights.append(w)
+        dist_start[p + 1] = len(weights)
+
+    d_pubs = _to_device(pubs)
+    d_groups = _to_device(np.array(group_rows, dtype=GROUP_DTYPE))
+    d_masks = _to_device(np.array(mask_limbs, dtype=np.uint64))
+    d_dist = _to_device(dist_start)
+    d_obs = _to_device(np.array(obs_limbs, dtype=np.uint64))
+    d_qpd = _to_device(np.array(qpd_limbs, dtype=np.uint64))
+    d_w = _to_device(np.array(weights, dtype=np.float64))
+    d_labels = _to_device(np.array(label_rows, dtype=LABEL_DTYPE))
+    d_ls = _to_device(np.array(lookup_start, dtype=np.uint32))
+    d_lk = _to_device(np.array(lookup_rows, dtype=SLOT_DTYPE).reshape(-1))
+    d_coeffs = _to_device(np.ascontiguousarray(coeffs[i_lo:i_hi], dtype=np.float64))
+    expvals = torch.zeros(max(tally_offset, 1), dtype=torch.float64, device="cuda")
+    out = torch.empty(max(n_obs, 1), dtype=torch.float64, device="cuda")
+    ws = torch.empty(max(lib.qcut_reduce_workspace_bytes(i_hi - i_lo, n_obs), 16), dtype=torch.uint8, device="cuda")
+    stream = _stream_ptr()
+    check(
+        lib.qcut_quasi_launch(
+            d_pubs.data_ptr(), len(pubs), d_groups.data_ptr(), d_masks.data_ptr(), d_dist.data_ptr(),
+            d_obs.data_ptr(), n_lo, d_qpd.data_ptr(), n_lq, d_w.data_ptr(), expvals.data_ptr(), stream,
+        ),
+        "qcut_quasi_launch",
+    )
+    check(
+        lib.qcut_reduce_expvals_launch(
+            expvals.data_ptr(), d_pubs.data_ptr(), d_labels.data_ptr(), len(label_rows), d_ls.data_ptr(),
+            d_lk.data_ptr(), d_coeffs.data_ptr(), i_hi - i_lo, n_obs, out.data_ptr(), ws.data_ptr(), stream,
+        ),
+        "qcut_reduce_expvals_launch",
+    )
+    return out[:n_obs]

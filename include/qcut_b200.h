@@ -20,7 +20,7 @@
  *     byte matrices, observable_measurements (shots x nb_obs) and qpd_measurements
  *     (shots x nb_qpd), exactly the bytes of Qiskit's BitArray.array: big-endian within a
  *     row (reference cutting_reconstruction.py:152-158).  Matrices start at 16-byte aligned
- *     offsets.
+ *     offsets and the buffer is readable up to the next multiple of 16 after each matrix.
  *   - masks: per group, n_terms x nb_obs bytes, big-endian rows (same memory order as the
  *     shot rows, so kernels AND raw bytes; reference utils/observable_grouping.py:140-151).
  *   - tallies: int64, tally[pub.tally_offset + t] = sum over shots of
@@ -37,17 +37,17 @@
 extern "C" {
 #endif
 
-#define QCUT_ABI_VERSION 1
-/* Shots per scheduling tile: tile_start[] handed to qcut_tally_launch counts tiles of this size. */
+#define QCUT_ABI_VERSION 2
+/* Shots per scheduling tile (one warp processes one tile of one PUB at a time). */
 #define QCUT_TILE_SHOTS 4096
 /* Widest observable row (bytes) the kernels accept: 64 bytes = 512 measured qubits per group. */
 #define QCUT_MAX_OBS_BYTES 64
 
 typedef enum qcut_status {
   QCUT_OK = 0,
-  QCUT_ERR_INVALID = -1,     /* bad argument (null pointer, size, unsupported width) */
-  QCUT_ERR_CUDA = -2,        /* a CUDA runtime call failed */
-  QCUT_ERR_JIT = -3,         /* NVRTC specialisation failed */
+  QCUT_ERR_INVALID = -1, /* bad argument (null pointer, size, unsupported width) */
+  QCUT_ERR_CUDA = -2,    /* a CUDA runtime call failed */
+  QCUT_ERR_JIT = -3,     /* NVRTC specialisation failed */
   QCUT_ERR_NOMEM = -4
 } qcut_status;
 
@@ -80,12 +80,13 @@ typedef struct qcut_slot {
 
 /* One subsystem ("partition label") as seen by the reduction kernel. */
 typedef struct qcut_label_desc {
-  uint64_t pub_base;     /* index of the label's first PUB in the pub table (local to this rank)   */
-  uint32_t num_groups;   /* G_label: PUB of (coefficient i, group g) is pub_base + i * G_label + g */
-  uint32_t lookup_base;  /* index into lookup_start[] of this label's first observable            */
+  uint64_t pub_base;    /* index of the label's first PUB in the pub table (local to this rank)   */
+  uint32_t num_groups;  /* G_label: PUB of (coefficient i, group g) is pub_base + i * G_label + g */
+  uint32_t lookup_base; /* index into lookup_start[] of this label's first observable            */
 } qcut_label_desc;
 
-typedef struct qcut_plan qcut_plan;
+typedef struct qcut_plan qcut_plan;         /* groups + masks in HBM, kernels specialised for them */
+typedef struct qcut_schedule qcut_schedule; /* PUB table in HBM + per-kernel tile lists            */
 
 int qcut_abi_version(void);
 const char* qcut_last_error(void);
@@ -93,27 +94,38 @@ const char* qcut_last_error(void);
 /* Number of visible CUDA devices (0 if none / no driver).  Never fails. */
 int qcut_device_count(void);
 
-/* ---- plan: group table + masks resident in HBM, plus kernels specialised for them -------------
+/* ---- plan ---------------------------------------------------------------------------------------
  * Replaces the per-call host state the reference builds at cutting_reconstruction.py:113-116.
- * flags: bit 0 = disable NVRTC specialisation (always use the generic kernel). */
+ * Every group is assigned one of the K1 kernels:
+ *   0 = generic (any width), 1 = bit-sliced with run-time masks, >= 2 = bit-sliced kernel
+ *   specialised by NVRTC for that group's masks (at most QCUT_MAX_JIT_KERNELS per plan, chosen
+ *   by term count; the rest use kernel 0/1).
+ * flags: QCUT_PLAN_NO_JIT disables NVRTC specialisation, QCUT_PLAN_GENERIC_ONLY forces kernel 0. */
 #define QCUT_PLAN_NO_JIT 1u
+#define QCUT_PLAN_GENERIC_ONLY 2u
+#define QCUT_MAX_JIT_KERNELS 8
 int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
                      size_t mask_bytes, unsigned flags, qcut_plan** out_plan);
 void qcut_plan_destroy(qcut_plan* plan);
-/* 0 = generic kernel, 1 = bit-sliced specialised kernel; <0 on error. */
 int qcut_plan_group_kernel(const qcut_plan* plan, int group);
-/* Copies the generated CUDA source of the specialised kernels (NUL terminated) into buf;
- * returns the full length needed.  For inspection (nvcc -Xptxas -v, cuobjdump) only. */
-size_t qcut_plan_source(const qcut_plan* plan, char* buf, size_t buf_len);
+/* Copies the generated CUDA source of specialised kernel `kernel` (>= 2), NUL terminated, into
+ * buf; returns the full length needed (0 if there is no such kernel).  For inspection only. */
+size_t qcut_plan_source(const qcut_plan* plan, int kernel, char* buf, size_t buf_len);
+
+/* ---- schedule -----------------------------------------------------------------------------------
+ * Copies the PUB table to HBM and cuts every PUB into tiles of QCUT_TILE_SHOTS consecutive shots,
+ * listed per kernel so that each K1 kernel streams only its own tiles. */
+int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int64_t n_pubs,
+                         qcut_schedule** out_schedule);
+void qcut_schedule_destroy(qcut_schedule* schedule);
+int64_t qcut_schedule_num_tiles(const qcut_schedule* schedule);
+const qcut_pub_desc* qcut_schedule_device_pubs(const qcut_schedule* schedule);
 
 /* ---- K1: parity tallies (reference cutting_reconstruction.py:152-161 + :196-222) -------------
- * Work is scheduled in tiles of QCUT_TILE_SHOTS consecutive shots of one PUB:
- *   d_tile_start[p] = number of tiles in PUBs 0..p-1 (n_pubs + 1 entries, last == n_tiles),
- *   d_tile_pub[t]   = PUB that owns tile t (n_tiles entries).
- * Zeroes d_tallies[0 .. n_tallies) and accumulates into it. */
-int qcut_tally_launch(const qcut_plan* plan, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
-                      int64_t n_pubs, const int64_t* d_tile_start, const uint32_t* d_tile_pub,
-                      int64_t n_tiles, int64_t* d_tallies, int64_t n_tallies, void* stream);
+ * Zeroes d_tallies[0 .. n_tallies) and accumulates the exact sign tallies of every PUB of the
+ * schedule into it.  Returns the number of kernels launched in *n_launches if not NULL. */
+int qcut_tally_launch(const qcut_plan* plan, const qcut_schedule* schedule, const uint8_t* d_data,
+                      int64_t* d_tallies, int64_t n_tallies, void* stream, int* n_launches);
 
 /* ---- K2: coefficient-weighted product over subsystems, summed over subexperiment tuples -------
  * (reference cutting_reconstruction.py:134-136,163-168):
@@ -154,12 +166,12 @@ int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const ui
                      int64_t n_arrays, void* h_dst, int n_threads);
 
 /* ---- host-only helpers (no GPU needed): inspection and CPU-side testing of the specialisation -----
- * qcut_generate_source: the CUDA translation unit qcut_plan_create would hand to NVRTC for these
- * groups; h_group_variant[g] receives the specialised-kernel variant of group g or -1 (generic
- * kernel).  Returns the length needed including the NUL, 0 on bad input or nothing to specialise.
+ * qcut_generate_source: the CUDA translation unit NVRTC receives when group `group` of this table
+ * is specialised.  Returns the length needed including the NUL; 0 if the group cannot be
+ * specialised (unsupported width / too many terms) or the input is invalid.
  * qcut_compile_source: NVRTC -> sm_100a cubin (size, and the image if cubin_buf is large enough). */
 size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
-                            size_t mask_bytes, int* h_group_variant, char* buf, size_t buf_len);
+                            size_t mask_bytes, int group, char* buf, size_t buf_len);
 int qcut_compile_source(const char* source, size_t* cubin_bytes, char* cubin_buf, size_t cubin_buf_len);
 
 #ifdef __cplusplus

@@ -19,8 +19,10 @@ LIB_PATH = PACKAGE_DIR / "libqcut_b200.so"
 
 TILE_SHOTS = 4096
 MAX_OBS_BYTES = 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 PLAN_NO_JIT = 1
+PLAN_GENERIC_ONLY = 2
+KERNEL_GENERIC, KERNEL_SLICED_RT, KERNEL_JIT0 = 0, 1, 2
 
 
 class QcutError(RuntimeError):
@@ -81,14 +83,18 @@ SIGNATURES = {
     "qcut_plan_create": (_INT, [_VP, _INT, _VP, _SZ, C.c_uint, C.POINTER(_VP)]),
     "qcut_plan_destroy": (None, [_VP]),
     "qcut_plan_group_kernel": (_INT, [_VP, _INT]),
-    "qcut_plan_source": (_SZ, [_VP, C.c_char_p, _SZ]),
-    "qcut_tally_launch": (_INT, [_VP, _VP, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _VP]),
+    "qcut_plan_source": (_SZ, [_VP, _INT, C.c_char_p, _SZ]),
+    "qcut_schedule_create": (_INT, [_VP, _VP, _I64, C.POINTER(_VP)]),
+    "qcut_schedule_destroy": (None, [_VP]),
+    "qcut_schedule_num_tiles": (_I64, [_VP]),
+    "qcut_schedule_device_pubs": (_VP, [_VP]),
+    "qcut_tally_launch": (_INT, [_VP, _VP, _VP, _VP, _I64, _VP, C.POINTER(_INT)]),
     "qcut_reduce_workspace_bytes": (_SZ, [_I64, _INT]),
     "qcut_reduce_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _VP]),
     "qcut_quasi_launch": (_INT, [_VP, _I64, _VP, _VP, _VP, _VP, _INT, _VP, _INT, _VP, _VP, _VP]),
     "qcut_reduce_expvals_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _VP]),
     "qcut_gather_host": (_INT, [_VP, _VP, _VP, _I64, _VP, _INT]),
-    "qcut_generate_source": (_SZ, [_VP, _INT, _VP, _SZ, _VP, C.c_char_p, _SZ]),
+    "qcut_generate_source": (_SZ, [_VP, _INT, _VP, _SZ, _INT, C.c_char_p, _SZ]),
     "qcut_compile_source": (_INT, [C.c_char_p, C.POINTER(_SZ), _VP, _SZ]),
 }
 
@@ -136,18 +142,18 @@ def np_ptr(a: np.ndarray) -> int:
     return a.ctypes.data
 
 
-def generate_source(groups: np.ndarray, masks: np.ndarray) -> tuple[str, np.ndarray]:
-    """CUDA source NVRTC would receive for these groups, and the variant of each group (-1 = generic)."""
+def generate_source(groups: np.ndarray, masks: np.ndarray, group: int) -> str:
+    """CUDA source NVRTC receives when ``group`` is specialised ('' if it cannot be)."""
     lib = load()
     groups = np.ascontiguousarray(groups, dtype=GROUP_DTYPE)
     masks = np.ascontiguousarray(masks, dtype=np.uint8)
-    variants = np.full(len(groups), -1, dtype=np.int32)
-    need = lib.qcut_generate_source(np_ptr(groups), len(groups), np_ptr(masks), masks.size, np_ptr(variants), None, 0)
+    mptr = np_ptr(masks) if masks.size else None
+    need = lib.qcut_generate_source(np_ptr(groups), len(groups), mptr, masks.size, group, None, 0)
     if need <= 1:
-        return "", variants
+        return ""
     buf = C.create_string_buffer(need)
-    lib.qcut_generate_source(np_ptr(groups), len(groups), np_ptr(masks), masks.size, np_ptr(variants), buf, need)
-    return buf.value.decode(), variants
+    lib.qcut_generate_source(np_ptr(groups), len(groups), mptr, masks.size, group, buf, need)
+    return buf.value.decode()
 
 
 def compile_source(source: str) -> bytes:

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <map>
 #include <new>
 #include <thread>
 
@@ -31,12 +32,16 @@ int sm_count() {
   return cached;
 }
 
-// defined in tally_generic.cu / reduce.cu / jit.cu
-int launch_tally_generic(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, const uint32_t*,
-                         const int64_t*, int64_t, int64_t*, cudaStream_t);
-int launch_tally_sliced(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, const uint32_t*,
-                        const int64_t*, int64_t, int64_t*, cudaStream_t);
-int jit_specialise(qcut_plan* plan);
+// defined in tally_generic.cu / tally_sliced.cu / reduce.cu / jit.cu
+int launch_tally_generic(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, const TileEntry*, int64_t,
+                         int64_t*, cudaStream_t);
+int launch_tally_sliced_rt(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, const TileEntry*, int64_t,
+                           int64_t*, cudaStream_t);
+int launch_tally_jit(const JitKernel&, const uint8_t*, const qcut_pub_desc*, const TileEntry*, int64_t, int64_t*,
+                     cudaStream_t);
+bool sliced_rt_supports(uint32_t nb_obs);
+bool jit_supports(const qcut_group_desc& gd);
+int jit_build(qcut_plan* plan);
 void jit_release(qcut_plan* plan);
 template <typename TallyT>
 int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, int, const uint32_t*,
@@ -44,6 +49,10 @@ int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, i
 size_t reduce_workspace_bytes(int64_t, int);
 int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const uint64_t*, const int64_t*,
                  const uint64_t*, int, const uint64_t*, int, const double*, double*, cudaStream_t);
+
+// Groups with at least this many terms are worth an NVRTC specialisation: below it the (shared)
+// load + transposition cost dominates and the run-time-mask kernel is within a few percent.
+constexpr uint32_t kJitMinTerms = 12;
 
 }  // namespace qcut
 
@@ -98,7 +107,7 @@ int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_
     dev.nb_obs = gd.nb_obs;
     dev.n_words = (gd.nb_obs + 3) / 4;
     dev.word_offset = (uint32_t)words.size();
-    dev.kernel = KERNEL_GENERIC;
+    dev.kernel = (!(flags & QCUT_PLAN_GENERIC_ONLY) && sliced_rt_supports(gd.nb_obs)) ? KERNEL_SLICED_RT : KERNEL_GENERIC;
     for (uint32_t t = 0; t < gd.n_terms; ++t) {
       const uint8_t* row = h_masks + gd.mask_offset + (size_t)t * gd.nb_obs;
       for (uint32_t w = 0; w < dev.n_words; ++w) {
@@ -109,16 +118,34 @@ int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_
     }
   }
 
-  if (!(flags & QCUT_PLAN_NO_JIT)) {
-    const int rc = jit_specialise(plan);  // marks groups_dev[g].kernel / variant, builds the module
+  // Pick the groups to specialise: the QCUT_MAX_JIT_KERNELS distinct (width, masks) sets with the
+  // most terms among those with >= kJitMinTerms terms.
+  if (!(flags & (QCUT_PLAN_NO_JIT | QCUT_PLAN_GENERIC_ONLY))) {
+    std::map<std::string, std::vector<int>> by_masks;
+    for (int g = 0; g < n_groups; ++g) {
+      const qcut_group_desc& gd = h_groups[g];
+      if (gd.n_terms < kJitMinTerms || !jit_supports(gd)) continue;
+      std::string key(reinterpret_cast<const char*>(&gd.nb_obs), sizeof(gd.nb_obs));
+      key.append(reinterpret_cast<const char*>(h_masks + gd.mask_offset), (size_t)gd.n_terms * gd.nb_obs);
+      by_masks[key].push_back(g);
+    }
+    std::vector<const std::vector<int>*> sets;
+    for (const auto& kv : by_masks) sets.push_back(&kv.second);
+    std::stable_sort(sets.begin(), sets.end(), [&](const std::vector<int>* a, const std::vector<int>* b) {
+      return h_groups[a->front()].n_terms > h_groups[b->front()].n_terms;
+    });
+    if (sets.size() > QCUT_MAX_JIT_KERNELS) sets.resize(QCUT_MAX_JIT_KERNELS);
+    for (const auto* set : sets) {
+      JitKernel jk;
+      jk.group = set->front();
+      for (int g : *set) plan->groups_dev[g].kernel = KERNEL_JIT0 + (uint32_t)plan->jit.size();
+      plan->jit.push_back(std::move(jk));
+    }
+    const int rc = jit_build(plan);
     if (rc != QCUT_OK) {
-      delete plan;
+      qcut_plan_destroy(plan);
       return rc;
     }
-  }
-  for (const GroupDev& dev : plan->groups_dev) {
-    plan->any_generic |= dev.kernel == KERNEL_GENERIC;
-    plan->any_sliced |= dev.kernel == KERNEL_SLICED;
   }
 
   auto fail = [&](cudaError_t err, const char* what) {
@@ -154,35 +181,106 @@ int qcut_plan_group_kernel(const qcut_plan* plan, int group) {
   return (int)plan->groups_dev[group].kernel;
 }
 
-size_t qcut_plan_source(const qcut_plan* plan, char* buf, size_t buf_len) {
-  if (!plan) return 0;
-  const size_t need = plan->jit_source.size() + 1;
+size_t qcut_plan_source(const qcut_plan* plan, int kernel, char* buf, size_t buf_len) {
+  if (!plan || kernel < (int)KERNEL_JIT0 || kernel >= plan->n_kernels()) return 0;
+  const std::string& src = plan->jit[kernel - KERNEL_JIT0].source;
   if (buf && buf_len) {
-    const size_t n = std::min(buf_len - 1, plan->jit_source.size());
-    std::memcpy(buf, plan->jit_source.data(), n);
+    const size_t n = std::min(buf_len - 1, src.size());
+    std::memcpy(buf, src.data(), n);
     buf[n] = '\0';
   }
-  return need;
+  return src.size() + 1;
 }
 
-int qcut_tally_launch(const qcut_plan* plan, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
-                      int64_t n_pubs, const int64_t* d_tile_start, const uint32_t* d_tile_pub,
-                      int64_t n_tiles, int64_t* d_tallies, int64_t n_tallies, void* stream) {
-  if (!plan) return set_error("qcut_tally_launch: plan is NULL"), QCUT_ERR_INVALID;
-  if (n_pubs < 0 || n_tiles < 0 || n_tallies < 0) return set_error("qcut_tally_launch: negative size"), QCUT_ERR_INVALID;
+int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int64_t n_pubs,
+                         qcut_schedule** out_schedule) {
+  if (!out_schedule) return set_error("qcut_schedule_create: out_schedule is NULL"), QCUT_ERR_INVALID;
+  *out_schedule = nullptr;
+  if (!plan || n_pubs < 0 || (n_pubs > 0 && !h_pubs)) return set_error("qcut_schedule_create: bad argument"), QCUT_ERR_INVALID;
+  if (n_pubs >= (int64_t)1 << 32) return set_error("qcut_schedule_create: more than 2^32 PUBs"), QCUT_ERR_INVALID;
+  const int nk = plan->n_kernels();
+  std::vector<int64_t> count(nk + 1, 0);
+  for (int64_t p = 0; p < n_pubs; ++p) {
+    if (h_pubs[p].group >= (uint32_t)plan->n_groups) {
+      set_error("qcut_schedule_create: PUB " + std::to_string(p) + " references group " + std::to_string(h_pubs[p].group) +
+                " but the plan has " + std::to_string(plan->n_groups));
+      return QCUT_ERR_INVALID;
+    }
+    const int64_t tiles = ((int64_t)h_pubs[p].shots + QCUT_TILE_SHOTS - 1) / QCUT_TILE_SHOTS;
+    count[plan->groups_dev[h_pubs[p].group].kernel + 1] += tiles;
+  }
+  for (int k = 0; k < nk; ++k) count[k + 1] += count[k];
+  qcut_schedule* sch = new (std::nothrow) qcut_schedule();
+  if (!sch) return set_error("qcut_schedule_create: out of host memory"), QCUT_ERR_NOMEM;
+  sch->n_pubs = n_pubs;
+  sch->n_tiles = count[nk];
+  sch->kernel_tile_begin = count;
+  std::vector<TileEntry> tiles((size_t)std::max<int64_t>(sch->n_tiles, 1));
+  std::vector<int64_t> cursor(count.begin(), count.end() - 1);
+  for (int64_t p = 0; p < n_pubs; ++p) {
+    const int64_t n = ((int64_t)h_pubs[p].shots + QCUT_TILE_SHOTS - 1) / QCUT_TILE_SHOTS;
+    int64_t& c = cursor[plan->groups_dev[h_pubs[p].group].kernel];
+    for (int64_t t = 0; t < n; ++t) tiles[(size_t)c++] = TileEntry{(uint32_t)p, (uint32_t)t};
+  }
+  auto fail = [&](cudaError_t err, const char* what) {
+    const int rc = cuda_fail(err, what);
+    qcut_schedule_destroy(sch);
+    return rc;
+  };
+  cudaError_t err = cudaMalloc(&sch->d_pubs, sizeof(qcut_pub_desc) * (size_t)std::max<int64_t>(n_pubs, 1));
+  if (err != cudaSuccess) return fail(err, "cudaMalloc(pubs)");
+  if (n_pubs) {
+    err = cudaMemcpy(sch->d_pubs, h_pubs, sizeof(qcut_pub_desc) * (size_t)n_pubs, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) return fail(err, "cudaMemcpy(pubs)");
+  }
+  err = cudaMalloc(&sch->d_tiles, sizeof(TileEntry) * tiles.size());
+  if (err != cudaSuccess) return fail(err, "cudaMalloc(tiles)");
+  if (sch->n_tiles) {
+    err = cudaMemcpy(sch->d_tiles, tiles.data(), sizeof(TileEntry) * (size_t)sch->n_tiles, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) return fail(err, "cudaMemcpy(tiles)");
+  }
+  *out_schedule = sch;
+  return QCUT_OK;
+}
+
+void qcut_schedule_destroy(qcut_schedule* schedule) {
+  if (!schedule) return;
+  if (schedule->d_pubs) cudaFree(schedule->d_pubs);
+  if (schedule->d_tiles) cudaFree(schedule->d_tiles);
+  delete schedule;
+}
+
+int64_t qcut_schedule_num_tiles(const qcut_schedule* schedule) { return schedule ? schedule->n_tiles : 0; }
+
+const qcut_pub_desc* qcut_schedule_device_pubs(const qcut_schedule* schedule) {
+  return schedule ? schedule->d_pubs : nullptr;
+}
+
+int qcut_tally_launch(const qcut_plan* plan, const qcut_schedule* schedule, const uint8_t* d_data,
+                      int64_t* d_tallies, int64_t n_tallies, void* stream, int* n_launches) {
+  if (n_launches) *n_launches = 0;
+  if (!plan || !schedule) return set_error("qcut_tally_launch: plan or schedule is NULL"), QCUT_ERR_INVALID;
+  if (n_tallies < 0) return set_error("qcut_tally_launch: negative size"), QCUT_ERR_INVALID;
   if (n_tallies > 0 && !d_tallies) return set_error("qcut_tally_launch: d_tallies is NULL"), QCUT_ERR_INVALID;
-  if (n_tiles > 0 && (!d_data || !d_pubs || !d_tile_start || !d_tile_pub)) return set_error("qcut_tally_launch: NULL input"), QCUT_ERR_INVALID;
+  if (schedule->n_tiles > 0 && !d_data) return set_error("qcut_tally_launch: d_data is NULL"), QCUT_ERR_INVALID;
+  if ((int)schedule->kernel_tile_begin.size() != plan->n_kernels() + 1)
+    return set_error("qcut_tally_launch: schedule was built for a different plan"), QCUT_ERR_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n_tallies > 0) QCUT_CUDA(cudaMemsetAsync(d_tallies, 0, sizeof(int64_t) * (size_t)n_tallies, s));
-  if (n_pubs == 0 || n_tiles == 0) return QCUT_OK;
-  if (plan->any_sliced) {
-    const int rc = launch_tally_sliced(plan, d_data, d_pubs, d_tile_pub, d_tile_start, n_tiles, d_tallies, s);
+  int launches = 0;
+  for (int k = 0; k < plan->n_kernels(); ++k) {
+    const int64_t begin = schedule->kernel_tile_begin[k];
+    const int64_t n = schedule->kernel_tile_begin[k + 1] - begin;
+    if (n <= 0) continue;
+    const TileEntry* tiles = schedule->d_tiles + begin;
+    int rc;
+    if (k == (int)KERNEL_GENERIC) rc = launch_tally_generic(plan, d_data, schedule->d_pubs, tiles, n, d_tallies, s);
+    else if (k == (int)KERNEL_SLICED_RT) rc = launch_tally_sliced_rt(plan, d_data, schedule->d_pubs, tiles, n, d_tallies, s);
+    else rc = launch_tally_jit(plan->jit[k - KERNEL_JIT0], d_data, schedule->d_pubs, tiles, n, d_tallies, s);
     if (rc != QCUT_OK) return rc;
+    ++launches;
   }
-  if (plan->any_generic) {
-    const int rc = launch_tally_generic(plan, d_data, d_pubs, d_tile_pub, d_tile_start, n_tiles, d_tallies, s);
-    if (rc != QCUT_OK) return rc;
-  }
+  if (n_launches) *n_launches = launches;
   return QCUT_OK;
 }
 

@@ -1,4 +1,4 @@
-// Shared device/host declarations for libqcut_b200 (sm_100a).
+// Shared host/device declarations for libqcut_b200 (sm_100a).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -11,43 +11,63 @@
 
 namespace qcut {
 
-// Per-group record in HBM.  `kernel` selects which K1 variant owns the group's tiles.
+// Per-group record in HBM.
 struct GroupDev {
   uint32_t n_terms;
   uint32_t nb_obs;
-  uint32_t n_words;       // ceil(nb_obs / 4): 32-bit words per (zero padded) row
-  uint32_t word_offset;   // index of the group's first mask word in mask_words[]
-  uint32_t kernel;        // 0 = generic, 1 = bit-sliced specialised
-  uint32_t variant;       // index of the specialised kernel body (switch case) when kernel == 1
-  uint32_t reserved[2];
+  uint32_t n_words;      // ceil(nb_obs / 4): 32-bit words per (zero padded) mask row
+  uint32_t word_offset;  // index of the group's first mask word in mask_words[]
+  uint32_t kernel;       // 0 = generic, 1 = bit-sliced run-time masks, >= 2 = NVRTC-specialised
+  uint32_t reserved[3];
 };
 
-enum : uint32_t { KERNEL_GENERIC = 0, KERNEL_SLICED = 1 };
+struct TileEntry {
+  uint32_t pub;
+  uint32_t tile_in_pub;
+};
+
+enum : uint32_t { KERNEL_GENERIC = 0, KERNEL_SLICED_RT = 1, KERNEL_JIT0 = 2 };
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t err, const char* what);
 
-#define QCUT_CUDA(call)                                        \
-  do {                                                         \
-    cudaError_t err__ = (call);                                \
+#define QCUT_CUDA(call)                                               \
+  do {                                                                \
+    cudaError_t err__ = (call);                                       \
     if (err__ != cudaSuccess) return ::qcut::cuda_fail(err__, #call); \
   } while (0)
 
 int sm_count();
+
+// One NVRTC-specialised kernel (jit.cu).
+struct JitKernel {
+  std::string source;
+  std::string log;
+  std::vector<char> cubin;
+  cudaLibrary_t library = nullptr;
+  cudaKernel_t kernel = nullptr;
+  int min_blocks = 2;
+  int group = -1;  // representative group
+};
 
 }  // namespace qcut
 
 struct qcut_plan {
   int n_groups = 0;
   unsigned flags = 0;
-  std::vector<qcut_group_desc> groups;      // host copy
-  std::vector<uint8_t> masks;               // host copy, big-endian rows
-  std::vector<qcut::GroupDev> groups_dev;   // host mirror of the device table
+  std::vector<qcut_group_desc> groups;     // host copy
+  std::vector<uint8_t> masks;              // host copy, big-endian rows
+  std::vector<qcut::GroupDev> groups_dev;  // host mirror of the device table
   qcut::GroupDev* d_groups = nullptr;
-  uint32_t* d_mask_words = nullptr;         // little-endian words assembled from the byte rows
-  bool any_generic = false;
-  bool any_sliced = false;
-  std::string jit_source;                   // generated CUDA source ("" when nothing was specialised)
-  std::string jit_log;
-  void* jit = nullptr;                      // qcut::JitModule*
+  uint32_t* d_mask_words = nullptr;        // little-endian words assembled from the byte rows
+  std::vector<qcut::JitKernel> jit;        // kernel id = KERNEL_JIT0 + index
+  int n_kernels() const { return (int)qcut::KERNEL_JIT0 + (int)jit.size(); }
+};
+
+struct qcut_schedule {
+  int64_t n_pubs = 0;
+  int64_t n_tiles = 0;
+  qcut_pub_desc* d_pubs = nullptr;
+  qcut::TileEntry* d_tiles = nullptr;      // sorted by kernel id, PUB order within a kernel
+  std::vector<int64_t> kernel_tile_begin;  // n_kernels + 1 offsets into d_tiles
 };

@@ -1,46 +1,56 @@
-// Hand-written body of the bit-sliced parity-tally kernel (K1 fast path, sm_100a).
+// Hand-written core of the bit-sliced parity-tally kernels (K1 fast paths, sm_100a).
 //
-// This text is compiled at plan-creation time by NVRTC together with one generated
-// `struct TermsN` per commuting observable group (its XOR network, masks baked in as
-// register names), see jit.cu.  It is also compiled by g++ with QCUT_HOST_EMU defined,
-// where tests/ emulate one lane at a time against the oracle.
+// Compiled three ways from this one text:
+//   * by nvcc into libqcut_b200.so for the run-time-mask kernel (tally_sliced.cu),
+//   * by NVRTC at plan-creation time, followed by one generated `struct Terms` holding a group's
+//     XOR network with the masks baked in as register names (jit.cu),
+//   * by g++ with QCUT_HOST_EMU defined, where tests/ emulate one lane at a time against the oracle.
 //
-// Idea: a lane owns 32 "rows" (32-bit words of shot data, loaded
-// with coalesced 128-bit loads), transposes the 32x32 bit block in registers so that
-// register i holds bit i of 32 different shots, and then evaluates every Pauli term as
-// XOR of a few such bit-planes: one LOP3 per <=2 planes and ONE popcount per 32 shots
-// per term, instead of the reference's AND + popcount per shot per term
-// (cutting_reconstruction.py:213-220).  Tallies are order independent, so any fixed
-// shot <-> (lane, row) assignment is valid as long as the qpd parity plane uses the
-// same one.
+// Idea: a lane owns 32 "rows" (32-bit words of shot data, loaded with
+// coalesced 128-bit loads), transposes the 32x32 bit block in registers so that register i holds
+// bit i of 32 different shots, and then evaluates every Pauli term as the XOR of a few such
+// bit-planes: ONE popcount per 32 shots per term instead of the reference's AND + popcount per
+// shot per term (cutting_reconstruction.py:213-220).  Tallies are order independent, so any
+// fixed shot <-> (lane, row) assignment is valid as long as the qpd parity plane uses the same one.
 //
 // Geometry of one step for NB-byte observable rows (each lane issues CHUNKS 16-byte loads):
 //   NB = 8: 16 chunks, rows 2k+e of block 0/1 = low/high word of shot 2*(32k+lane)+e, 1024 shots
 //   NB = 4:  8 chunks, row 4k+e = shot 4*(32k+lane)+e,                                 1024 shots
 //   NB = 2:  8 chunks, row 4k+e holds shots 8*(32k+lane)+2e+{0,1}  (2 batches),        2048 shots
 //   NB = 1:  8 chunks, row 4k+e holds shots 16*(32k+lane)+4e+{0..3} (4 batches),       4096 shots
-// After the transposition, plane (byte B, bit b) of batch u is register 8*(B%4)+b (+ (32/BATCHES)*u)
-// of block B/4.
+// After the transposition, plane (byte B, bit b) of batch u is register 8*(B%4)+b + PLANES*u of
+// block B/4, i.e. "memory bit" 8*B+b of the row: masks are used in memory order, never byte swapped.
+#pragma once
 
-#ifndef QCUT_HOST_EMU
+#if defined(QCUT_HOST_EMU)
+#define QCUT_DEV static inline
+#define QCUT_MDEV inline
+#elif defined(__CUDACC_RTC__)
 typedef unsigned char uint8_t;
 typedef unsigned short uint16_t;
 typedef unsigned int uint32_t;
 typedef unsigned long long uint64_t;
 typedef long long int64_t;
 #define QCUT_DEV __device__ __forceinline__
+#define QCUT_MDEV __device__ __forceinline__
 #else
-#define QCUT_DEV static inline
+#include <stdint.h>
+#define QCUT_DEV __device__ __forceinline__
+#define QCUT_MDEV __device__ __forceinline__
 #endif
 
+#ifndef QCUT_TILE_SHOTS
 #define QCUT_TILE_SHOTS 4096
+#endif
 
-struct qcut_pub_desc {
+// Device-side mirrors of include/qcut_b200.h (NVRTC has no access to that header).
+struct QcutPub {
   uint64_t obs_offset, qpd_offset, tally_offset;
   uint32_t shots, group, nb_qpd, reserved;
 };
-struct GroupDev {
-  uint32_t n_terms, nb_obs, n_words, word_offset, kernel, variant, reserved[2];
+struct QcutTile {
+  uint32_t pub;          // PUB that owns the tile
+  uint32_t tile_in_pub;  // shots [tile_in_pub * QCUT_TILE_SHOTS, ...) of that PUB
 };
 
 struct qcut_u4 { uint32_t x, y, z, w; };
@@ -112,13 +122,13 @@ QCUT_DEV uint32_t qcut_byte_parity(uint32_t v) {
 
 template <int NB>
 struct QcutGeo {
-  static const int CHUNKS = (NB == 8) ? 16 : 8;      // 16-byte loads per lane per step
-  static const int BLOCKS = (NB == 8) ? 2 : 1;       // 32x32 blocks per lane per step
+  static const int CHUNKS = (NB == 8) ? 16 : 8;       // 16-byte loads per lane per step
+  static const int BLOCKS = (NB == 8) ? 2 : 1;        // 32x32 blocks per lane per step
   static const int BATCHES = (NB >= 4) ? 1 : 4 / NB;  // 32-shot batches per block
-  static const int SPC = 16 / NB;                    // shots per chunk
-  static const int RPC = (NB == 8) ? 2 : 4;          // rows per chunk (per block)
+  static const int SPC = 16 / NB;                     // shots per chunk
+  static const int RPC = (NB == 8) ? 2 : 4;           // rows per chunk (per block)
   static const int STEP_SHOTS = CHUNKS * 32 * SPC;
-  static const int PLANES = 32 / BATCHES;            // registers per batch in block 0
+  static const int PLANES = 32 / BATCHES;             // registers per batch in one block
 };
 
 // Shot (relative to the step) held by row j, sub-shot u of this lane.
@@ -146,118 +156,142 @@ QCUT_DEV void qcut_qp_slow(const uint8_t* __restrict__ qpd_s, int nbq, int n, in
   }
 }
 
-// One tile (<= QCUT_TILE_SHOTS shots of one PUB) for one lane.  acc[] receives, packed four
-// 8-bit fields per word, the number of odd-parity shots this lane saw for every term
-// (<= 128 per tile, so the fields cannot overflow).
+// One step (n <= STEP_SHOTS shots starting at obs_s / qpd_s) for one lane:
+//   a[blk][.]  <- bit-planes of the observable rows of this lane's shots,
+//   qp[u]      <- bit j = parity of ALL bits of the qpd row of the shot in row j, batch u
+//                 (reference cutting_reconstruction.py:213: pad bits above num_bits count too).
+// Rows past the end of the PUB are forced to zero (they then count as "even" and are removed
+// again by tally = n - 2 * odd).
+template <int NB>
+QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __restrict__ qpd_s, int nbq, int n,
+                        int lane, uint32_t (*a)[32], uint32_t* qp) {
+  typedef QcutGeo<NB> G;
+  // ---- coalesced 128-bit loads of the observable rows ------------------------------------
+#pragma unroll
+  for (int k = 0; k < G::CHUNKS; ++k) {
+    const int idx = k * 32 + lane;
+    qcut_u4 v = {0u, 0u, 0u, 0u};
+    if (idx * G::SPC < n) v = qcut_ld16(obs_s + (uint64_t)idx * 16);
+    if constexpr (NB == 8) {
+      a[0][2 * k] = v.x; a[1][2 * k] = v.y;
+      a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
+    } else {
+      a[0][4 * k] = v.x; a[0][4 * k + 1] = v.y; a[0][4 * k + 2] = v.z; a[0][4 * k + 3] = v.w;
+    }
+  }
+
+  // ---- qpd parity plane(s) -----------------------------------------------------------------
+#pragma unroll
+  for (int u = 0; u < G::BATCHES; ++u) qp[u] = 0;
+  if (nbq != 1) {
+    // Any other qpd row width: per-shot byte loop (rare: more than 8 cut measurements).
+    qcut_qp_slow<NB>(qpd_s, nbq, n, lane, qp);
+  } else if constexpr (NB == 1) {
+    // Same geometry as the observable rows: transpose the qpd block too, XOR its 8 planes.
+    uint32_t q[32];
+#pragma unroll
+    for (int k = 0; k < G::CHUNKS; ++k) {
+      const int idx = k * 32 + lane;
+      qcut_u4 v = {0u, 0u, 0u, 0u};
+      if (idx * G::SPC < n) v = qcut_ld16(qpd_s + (uint64_t)idx * 16);
+      q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
+    }
+    qcut_transpose32(q);
+#pragma unroll
+    for (int u = 0; u < G::BATCHES; ++u) {
+      uint32_t x = 0;
+#pragma unroll
+      for (int b = 0; b < G::PLANES; ++b) x ^= q[u * G::PLANES + b];
+      qp[u] = x;
+    }
+  } else {
+    // One qpd byte per shot: fold each byte to its parity, then gather the parity bits of
+    // four bytes with one multiply (no carries: all partial products hit distinct bits).
+#pragma unroll
+    for (int k = 0; k < G::CHUNKS; ++k) {
+      const int idx = k * 32 + lane;
+      if constexpr (NB == 8) {
+        if (k & 1) continue;  // chunks k, k+1 -> rows 2k .. 2k+3
+        uint32_t w = 0;
+        if (idx * 2 < n) w = qcut_ld2(qpd_s + (uint64_t)idx * 2);
+        if ((idx + 32) * 2 < n) w |= qcut_ld2(qpd_s + (uint64_t)(idx + 32) * 2) << 16;
+        const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
+        qp[0] |= nib << (2 * k);
+      } else if constexpr (NB == 4) {
+        uint32_t w = 0;
+        if (idx * 4 < n) w = qcut_ld4(qpd_s + (uint64_t)idx * 4);
+        const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
+        qp[0] |= nib << (4 * k);
+      } else {  // NB == 2: bytes (b0, b2) of each word -> batch 0, (b1, b3) -> batch 1
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t w = 0;
+          if (idx * 8 + 4 * h < n) w = qcut_ld4(qpd_s + (uint64_t)idx * 8 + 4 * h);
+          const uint32_t r = (qcut_byte_parity(w) * 0x01100220u) >> 24;
+          qp[0] |= (r & 3u) << (4 * k + 2 * h);
+          qp[G::BATCHES - 1] |= ((r >> 4) & 3u) << (4 * k + 2 * h);
+        }
+      }
+    }
+  }
+
+  // ---- bit-slice ---------------------------------------------------------------------------
+#pragma unroll
+  for (int blk = 0; blk < G::BLOCKS; ++blk) qcut_transpose32(a[blk]);
+
+  if (n != G::STEP_SHOTS) {
+    // Tail step: rows past the end of the PUB may hold bytes of the padding / next matrix.
+#pragma unroll
+    for (int u = 0; u < G::BATCHES; ++u) {
+      uint32_t valid = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) valid |= (uint32_t)(qcut_shot_of<NB>(j, u, lane) < n) << j;
+      qp[u] &= valid;
+#pragma unroll
+      for (int blk = 0; blk < G::BLOCKS; ++blk)
+#pragma unroll
+        for (int b = 0; b < G::PLANES; ++b) a[blk][u * G::PLANES + b] &= valid;
+    }
+  }
+}
+
+// ---- term engine A: masks baked into generated code (struct Terms from jit.cu) -----------------
+// acc[] receives, packed four 8-bit fields per word, the number of odd-parity shots this lane
+// saw for every term (<= 128 per tile, so the fields cannot overflow).
 template <int NB, class Terms>
 QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq,
                              int ns, int lane, uint32_t* acc) {
   typedef QcutGeo<NB> G;
 #pragma unroll
   for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
-
   for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
     const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
-    const bool full = n == G::STEP_SHOTS;
-    const uint8_t* __restrict__ obs_s = obs + (uint64_t)s0 * NB;
-    const uint8_t* __restrict__ qpd_s = qpd + (uint64_t)s0 * nbq;
-
-    // ---- coalesced 128-bit loads of the observable rows ------------------------------------
     uint32_t a[G::BLOCKS][32];
-#pragma unroll
-    for (int k = 0; k < G::CHUNKS; ++k) {
-      const int idx = k * 32 + lane;
-      qcut_u4 v = {0u, 0u, 0u, 0u};
-      if (idx * G::SPC < n) v = qcut_ld16(obs_s + (uint64_t)idx * 16);
-      if constexpr (NB == 8) {
-        a[0][2 * k] = v.x; a[1][2 * k] = v.y;
-        a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
-      } else {
-        a[0][4 * k] = v.x; a[0][4 * k + 1] = v.y; a[0][4 * k + 2] = v.z; a[0][4 * k + 3] = v.w;
-      }
-    }
-
-    // ---- qpd parity plane(s): bit j of qp[u] = parity of ALL bits of the qpd row of the shot
-    //      in row j, batch u (reference cutting_reconstruction.py:213) -------------------------
     uint32_t qp[G::BATCHES];
-#pragma unroll
-    for (int u = 0; u < G::BATCHES; ++u) qp[u] = 0;
-    if (nbq != 1) {
-      // Any other qpd row width: per-shot byte loop (rare: more than 8 cut measurements).
-      qcut_qp_slow<NB>(qpd_s, nbq, n, lane, qp);
-    } else if constexpr (NB == 1) {
-      // Same geometry as the observable rows: transpose the qpd block too, XOR its 8 planes.
-      uint32_t q[32];
-#pragma unroll
-      for (int k = 0; k < G::CHUNKS; ++k) {
-        const int idx = k * 32 + lane;
-        qcut_u4 v = {0u, 0u, 0u, 0u};
-        if (idx * G::SPC < n) v = qcut_ld16(qpd_s + (uint64_t)idx * 16);
-        q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
-      }
-      qcut_transpose32(q);
-#pragma unroll
-      for (int u = 0; u < G::BATCHES; ++u) {
-        uint32_t x = 0;
-#pragma unroll
-        for (int b = 0; b < G::PLANES; ++b) x ^= q[u * G::PLANES + b];
-        qp[u] = x;
-      }
-    } else {
-      // One qpd byte per shot: fold each byte to its parity, then gather the parity bits of
-      // four bytes with one multiply (no carries: all partial products hit distinct bits).
-#pragma unroll
-      for (int k = 0; k < G::CHUNKS; ++k) {
-        const int idx = k * 32 + lane;
-        if constexpr (NB == 8) {
-          if (k & 1) continue;  // chunks k, k+1 -> rows 2k .. 2k+3
-          uint32_t w = 0;
-          if (idx * 2 < n) w = qcut_ld2(qpd_s + (uint64_t)idx * 2);
-          if ((idx + 32) * 2 < n) w |= qcut_ld2(qpd_s + (uint64_t)(idx + 32) * 2) << 16;
-          const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
-          qp[0] |= nib << (2 * k);
-        } else if constexpr (NB == 4) {
-          uint32_t w = 0;
-          if (idx * 4 < n) w = qcut_ld4(qpd_s + (uint64_t)idx * 4);
-          const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
-          qp[0] |= nib << (4 * k);
-        } else {  // NB == 2: bytes (b0, b2) of each word -> batch 0, (b1, b3) -> batch 1
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t w = 0;
-            if (idx * 8 + 4 * h < n) w = qcut_ld4(qpd_s + (uint64_t)idx * 8 + 4 * h);
-            const uint32_t r = (qcut_byte_parity(w) * 0x01100220u) >> 24;
-            qp[0] |= (r & 3u) << (4 * k + 2 * h);
-            qp[G::BATCHES - 1] |= ((r >> 4) & 3u) << (4 * k + 2 * h);
-          }
-        }
-      }
-    }
-
-    // ---- bit-slice ---------------------------------------------------------------------------
-#pragma unroll
-    for (int blk = 0; blk < G::BLOCKS; ++blk) qcut_transpose32(a[blk]);
-
-    if (!full) {
-      // Tail step: rows past the end of the PUB may hold bytes of the padding / next matrix.
-#pragma unroll
-      for (int u = 0; u < G::BATCHES; ++u) {
-        uint32_t valid = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) valid |= (uint32_t)(qcut_shot_of<NB>(j, u, lane) < n) << j;
-        qp[u] &= valid;
-#pragma unroll
-        for (int blk = 0; blk < G::BLOCKS; ++blk)
-#pragma unroll
-          for (int b = 0; b < G::PLANES; ++b) a[blk][u * G::PLANES + b] &= valid;
-      }
-    }
-
-    // ---- per-term XOR network + one popcount per 32 shots per term ---------------------------
+    qcut_step<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
 #pragma unroll
     for (int u = 0; u < G::BATCHES; ++u)
       Terms::run(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], acc);
   }
+}
+
+// ---- term engine B: run-time masks, bit-planes parked in shared memory -------------------------
+// planes[p * 32] is this lane's word of memory-bit plane p (the caller passes the lane's column).
+// mask words are the little-endian words of the mask row in memory order (plan table).
+// Returns popcount of the parity word of term t for this lane's 32 shots.
+QCUT_DEV uint32_t qcut_rt_term(const uint32_t* planes, uint32_t qp, uint32_t m_lo, uint32_t m_hi) {
+  uint32_t x = qp;
+  while (m_lo) {
+    const int p = __ffs((int)m_lo) - 1;
+    m_lo &= m_lo - 1;
+    x ^= planes[p * 32];
+  }
+  while (m_hi) {
+    const int p = __ffs((int)m_hi) - 1;
+    m_hi &= m_hi - 1;
+    x ^= planes[(32 + p) * 32];
+  }
+  return (uint32_t)__popc(x);
 }
 
 #ifndef QCUT_HOST_EMU

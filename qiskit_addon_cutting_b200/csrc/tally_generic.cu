@@ -4,20 +4,19 @@
 // (_process_outcome_v2, :196-222).  One warp owns one tile of QCUT_TILE_SHOTS shots of one PUB;
 // each lane owns one shot per step, keeps the whole observable row in registers, and every term
 // costs one AND/XOR per 32-bit word, one POPC and one warp vote.  This is the always-available
-// path (odd row widths, groups the bit-sliced kernel does not cover) and the on-device golden
-// reference for the specialised kernels.  It is POPC-bound for many-term groups; the bit-sliced
-// kernel (jit.cu) is the fast path.
+// path (rows wider than the bit-sliced kernels cover) and the on-device golden reference for
+// them (QCUT_PLAN_GENERIC_ONLY).  It is POPC-bound for many-term groups.
 #include "common.cuh"
 
 namespace qcut {
 
 constexpr int kWarpsPerCta = 8;
-constexpr int kTermChunk = 256;                       // per-warp smem accumulators per pass
-constexpr int kMaxWords = QCUT_MAX_OBS_BYTES / 4;     // 16 words = 64 bytes per row
+constexpr int kTermChunk = 256;                    // per-warp smem accumulators per pass
+constexpr int kMaxWords = QCUT_MAX_OBS_BYTES / 4;  // 16 words = 64 bytes per row
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 tally_generic_kernel(const uint8_t* __restrict__ data, const qcut_pub_desc* __restrict__ pubs,
-                     const uint32_t* __restrict__ tile_pub, const int64_t* __restrict__ tile_start, int64_t n_tiles,
+                     const TileEntry* __restrict__ tiles, int64_t n_tiles,
                      const GroupDev* __restrict__ groups, const uint32_t* __restrict__ mask_words,
                      unsigned long long* __restrict__ tallies) {
   __shared__ int s_odd[kWarpsPerCta][kTermChunk];
@@ -26,12 +25,11 @@ tally_generic_kernel(const uint8_t* __restrict__ data, const qcut_pub_desc* __re
   const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
 
   for (int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + warp; tile < n_tiles; tile += n_warps) {
-    const uint32_t p = __ldg(tile_pub + tile);
-    const qcut_pub_desc pub = pubs[p];
+    const TileEntry te = tiles[tile];
+    const qcut_pub_desc pub = pubs[te.pub];
     const GroupDev grp = groups[pub.group];
-    if (grp.kernel != KERNEL_GENERIC) continue;  // owned by the specialised kernel
 
-    const int64_t shot0 = (tile - __ldg(tile_start + p)) * QCUT_TILE_SHOTS;
+    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;
     const int ns = (int)min((int64_t)QCUT_TILE_SHOTS, (int64_t)pub.shots - shot0);
     const int nb = (int)grp.nb_obs;
     const int nbq = (int)pub.nb_qpd;
@@ -91,14 +89,13 @@ tally_generic_kernel(const uint8_t* __restrict__ data, const qcut_pub_desc* __re
 }
 
 int launch_tally_generic(const qcut_plan* plan, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
-                         const uint32_t* d_tile_pub, const int64_t* d_tile_start, int64_t n_tiles,
-                         int64_t* d_tallies, cudaStream_t stream) {
+                         const TileEntry* d_tiles, int64_t n_tiles, int64_t* d_tallies, cudaStream_t stream) {
   if (n_tiles <= 0) return QCUT_OK;
   const int64_t want = (n_tiles + kWarpsPerCta - 1) / kWarpsPerCta;
   const int64_t cap = (int64_t)sm_count() * 8;  // 8 CTAs x 8 warps resident per SM
   const int grid = (int)(want < cap ? want : cap);
   tally_generic_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(
-      d_data, d_pubs, d_tile_pub, d_tile_start, n_tiles, plan->d_groups, plan->d_mask_words,
+      d_data, d_pubs, d_tiles, n_tiles, plan->d_groups, plan->d_mask_words,
       reinterpret_cast<unsigned long long*>(d_tallies));
   QCUT_CUDA(cudaGetLastError());
   return QCUT_OK;

@@ -16,7 +16,7 @@ Objects are recognised by protocol, so real Qiskit objects and the stand-ins of
 
 from __future__ import annotations
 
-from collections.abc import Hashable, Mapping, Sequence
+from collections.abc import Mapping, Sequence
 
 import numpy as np
 
@@ -110,10 +110,11 @@ def reconstruct_expectation_values(
         coefficients: ``(coefficient, WeightType)`` per unique subexperiment sample; only the
             float is used (reference ``:168``).
         observables: a ``PauliList`` or a dict mapping partition labels to ``PauliList``\ s.
-        process_group: optional ``torch.distributed`` process group.  When given (or when the
-            default group is initialised with world size > 1) every rank must make the same call;
-            each rank processes a contiguous slice of ``coefficients`` and the partial sums are
-            all-reduced over NCCL, so every rank returns the full result.
+        process_group: optional ``torch.distributed`` process group (e.g. ``dist.group.WORLD``).
+            When given, every rank must make the same call; each rank processes a contiguous
+            slice of ``coefficients`` (for every subsystem) and the partial sums are all-reduced
+            over NCCL, so every rank returns the full result.  Without it the call is
+            single-process, exactly like the reference.
 
     Returns:
         ``list`` of ``numpy.float64``, one expectation value per input observable.

@@ -14,7 +14,8 @@ import torch.distributed as dist
 
 
 def rank_and_world(process_group=None) -> tuple[int, int]:
-    if not (dist.is_available() and dist.is_initialized()):
+    """Sharding is opt-in: without an explicit process group the call is single-process (drop-in behaviour)."""
+    if process_group is None or not (dist.is_available() and dist.is_initialized()):
         return 0, 1
     return dist.get_rank(process_group), dist.get_world_size(process_group)
 

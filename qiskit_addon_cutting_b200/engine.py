@@ -44,7 +44,7 @@ def _to_device(a: np.ndarray) -> torch.Tensor:
 # Plan: group table + masks in HBM, kernels specialised by NVRTC (cached per mask set)
 # ------------------------------------------------------------------------------------------------
 class Plan:
-    def __init__(self, groups: np.ndarray, masks: np.ndarray, *, jit: bool = True):
+    def __init__(self, groups: np.ndarray, masks: np.ndarray, *, flags: int = 0):
         _lib.require_device()
         self.groups = np.ascontiguousarray(groups, dtype=GROUP_DTYPE)
         self.masks = np.ascontiguousarray(masks, dtype=np.uint8).reshape(-1)
@@ -55,7 +55,7 @@ class Plan:
                 len(self.groups),
                 _lib.np_ptr(self.masks) if self.masks.size else None,
                 self.masks.size,
-                0 if jit else _lib.PLAN_NO_JIT,
+                flags,
                 C.byref(handle),
             ),
             "qcut_plan_create",
@@ -66,11 +66,16 @@ class Plan:
     def kernel_of(self, group: int) -> int:
         return _lib.load().qcut_plan_group_kernel(self.handle, group)
 
-    def source(self) -> str:
+    def kernels(self) -> list[int]:
+        return [self.kernel_of(g) for g in range(len(self.groups))]
+
+    def source(self, kernel: int) -> str:
         lib = _lib.load()
-        need = lib.qcut_plan_source(self.handle, None, 0)
+        need = lib.qcut_plan_source(self.handle, kernel, None, 0)
+        if need == 0:
+            return ""
         buf = C.create_string_buffer(need)
-        lib.qcut_plan_source(self.handle, buf, need)
+        lib.qcut_plan_source(self.handle, kernel, buf, need)
         return buf.value.decode()
 
     def __del__(self):
@@ -86,14 +91,14 @@ _plan_cache: dict = {}
 _plan_lock = threading.Lock()
 
 
-def get_plan(groups: np.ndarray, masks: np.ndarray, *, jit: bool = True) -> Plan:
-    key = (torch.cuda.current_device(), jit, groups.tobytes(), masks.tobytes())
+def get_plan(groups: np.ndarray, masks: np.ndarray, *, flags: int = 0) -> Plan:
+    key = (torch.cuda.current_device(), flags, groups.tobytes(), masks.tobytes())
     with _plan_lock:
         plan = _plan_cache.get(key)
         if plan is None:
             if len(_plan_cache) >= 16:
                 _plan_cache.pop(next(iter(_plan_cache)))
-            plan = _plan_cache[key] = Plan(groups, masks, jit=jit)
+            plan = _plan_cache[key] = Plan(groups, masks, flags=flags)
         return plan
 
 
@@ -118,18 +123,10 @@ class HostTables:
     n_obs: int
     n_tallies: int
     data_bytes: int
-    tile_start: np.ndarray = field(default=None)  # int64 [n_pubs + 1]
-    tile_pub: np.ndarray = field(default=None)  # uint32 [n_tiles]
-
-    def finalize_tiles(self) -> None:
-        tiles = (self.pubs["shots"].astype(np.int64) + TILE_SHOTS - 1) // TILE_SHOTS
-        self.tile_start = np.zeros(len(self.pubs) + 1, dtype=np.int64)
-        np.cumsum(tiles, out=self.tile_start[1:])
-        self.tile_pub = np.repeat(np.arange(len(self.pubs), dtype=np.uint32), tiles)
 
     @property
     def n_tiles(self) -> int:
-        return int(self.tile_start[-1])
+        return int(((self.pubs["shots"].astype(np.int64) + TILE_SHOTS - 1) // TILE_SHOTS).sum())
 
     @property
     def work(self) -> int:
@@ -196,23 +193,45 @@ class TableBuilder:
             n_tallies=n_tallies,
             data_bytes=data_bytes,
         )
-        t.finalize_tiles()
         return t
 
 
 # ------------------------------------------------------------------------------------------------
 # Device batch: tables + shot bytes resident in HBM, and the two launches
 # ------------------------------------------------------------------------------------------------
+class Schedule:
+    """PUB table in HBM + per-kernel tile lists (``qcut_schedule``)."""
+
+    def __init__(self, plan: Plan, pubs: np.ndarray):
+        self.pubs = np.ascontiguousarray(pubs, dtype=PUB_DTYPE)
+        handle = C.c_void_p()
+        check(
+            _lib.load().qcut_schedule_create(
+                plan.handle, _lib.np_ptr(self.pubs) if len(self.pubs) else None, len(self.pubs), C.byref(handle)
+            ),
+            "qcut_schedule_create",
+        )
+        self.handle = handle
+        self.n_tiles = _lib.load().qcut_schedule_num_tiles(handle)
+        self.d_pubs = _lib.load().qcut_schedule_device_pubs(handle)
+
+    def __del__(self):
+        handle, self.handle = getattr(self, "handle", None), None
+        if handle:
+            try:
+                _lib.load().qcut_schedule_destroy(handle)
+            except Exception:  # interpreter shutdown
+                pass
+
+
 class DeviceBatch:
     """One rank's share of a reconstruction, resident in HBM."""
 
-    def __init__(self, tables: HostTables, data: torch.Tensor, *, jit: bool = True):
+    def __init__(self, tables: HostTables, data: torch.Tensor, *, flags: int = 0):
         self.tables = tables
-        self.plan = get_plan(tables.groups, tables.masks, jit=jit)
+        self.plan = get_plan(tables.groups, tables.masks, flags=flags)
+        self.schedule = Schedule(self.plan, tables.pubs)
         self.data = data
-        self.pubs = _to_device(tables.pubs)
-        self.tile_start = _to_device(tables.tile_start)
-        self.tile_pub = _to_device(tables.tile_pub)
         self.labels = _to_device(tables.labels)
         self.lookup_start = _to_device(tables.lookup_start)
         self.lookup = _to_device(tables.lookup)
@@ -221,33 +240,33 @@ class DeviceBatch:
         self.out = torch.empty(max(tables.n_obs, 1), dtype=torch.float64, device="cuda")
         ws = _lib.load().qcut_reduce_workspace_bytes(len(tables.coeffs), tables.n_obs)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device="cuda")
+        self.tally_launches = 0
 
-    def launch_tally(self) -> None:
-        """K1 on the current stream: exact int64 sign tallies of every (PUB, term)."""
-        t = self.tables
+    def launch_tally(self) -> int:
+        """K1 on the current stream: exact int64 sign tallies of every (PUB, term).  Returns #kernels launched."""
+        n = C.c_int(0)
         check(
             _lib.load().qcut_tally_launch(
                 self.plan.handle,
+                self.schedule.handle,
                 self.data.data_ptr(),
-                self.pubs.data_ptr(),
-                len(t.pubs),
-                self.tile_start.data_ptr(),
-                self.tile_pub.data_ptr(),
-                t.n_tiles,
                 self.tallies.data_ptr(),
-                t.n_tallies,
+                self.tables.n_tallies,
                 _stream_ptr(),
+                C.byref(n),
             ),
             "qcut_tally_launch",
         )
+        self.tally_launches = n.value
+        return n.value
 
-    def launch_reduce(self) -> None:
-        """K2 on the current stream: this rank's partial ``out[k]``."""
+    def launch_reduce(self) -> int:
+        """K2 on the current stream: this rank's partial ``out[k]``.  Returns #kernels launched (2)."""
         t = self.tables
         check(
             _lib.load().qcut_reduce_launch(
                 self.tallies.data_ptr(),
-                self.pubs.data_ptr(),
+                self.schedule.d_pubs,
                 self.labels.data_ptr(),
                 len(t.labels),
                 self.lookup_start.data_ptr(),
@@ -261,6 +280,7 @@ class DeviceBatch:
             ),
             "qcut_reduce_launch",
         )
+        return 2 if t.n_obs > 0 else 0
 
     def run(self) -> torch.Tensor:
         self.launch_tally()
@@ -306,10 +326,12 @@ def _pub_arrays(pub) -> tuple[np.ndarray, np.ndarray]:
     return obs, qpd
 
 
-def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
-             *, jit: bool = True) -> DeviceBatch:
-    """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM."""
-    _lib.require_device()
+def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int,
+                      n_obs: int) -> tuple[HostTables, list[np.ndarray]]:
+    """Walk the PUBs of coefficient range ``[i_lo, i_hi)`` of every label (host only, no device).
+
+    Returns the tables and the borrowed ``[obs_0, qpd_0, obs_1, qpd_1, ...]`` arrays in PUB order.
+    """
     builder = TableBuilder(n_obs)
     arrays: list[np.ndarray] = []
     pub_rows = []
@@ -336,24 +358,34 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
     pubs = np.array(pub_rows, dtype=PUB_DTYPE) if pub_rows else np.zeros(0, dtype=PUB_DTYPE)
     if len(pubs) and int(pubs["shots"].max()) >= 2**31:
         raise ValueError("A PUB with 2**31 or more shots is not supported.")
-    tables = builder.tables(pubs, coeffs[i_lo:i_hi], tally_offset, offset)
+    return builder.tables(pubs, coeffs[i_lo:i_hi], tally_offset, max(offset, _ALIGN)), arrays
 
+
+def gather_arrays(tables: HostTables, arrays: list[np.ndarray], dst_ptr: int, n_threads: int = 0) -> None:
+    """Copy every borrowed buffer to its offset in the staging buffer at ``dst_ptr`` (threads in C)."""
+    n = len(arrays)
+    if n == 0:
+        return
+    src = np.fromiter((a.ctypes.data for a in arrays), dtype=np.uint64, count=n)
+    nbytes = np.fromiter((a.nbytes for a in arrays), dtype=np.uint64, count=n)
+    dst = np.empty(n, dtype=np.uint64)
+    dst[0::2] = tables.pubs["obs_offset"]
+    dst[1::2] = tables.pubs["qpd_offset"]
+    check(
+        _lib.load().qcut_gather_host(_lib.np_ptr(src), _lib.np_ptr(nbytes), _lib.np_ptr(dst), n, dst_ptr, n_threads),
+        "qcut_gather_host",
+    )
+
+
+def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
+             *, flags: int = 0) -> DeviceBatch:
+    """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM."""
+    _lib.require_device()
+    tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs)
     # Gather every borrowed buffer into one pinned staging buffer (threads), then one H2D copy.
-    total = max(offset, _ALIGN)
+    total = tables.data_bytes
     pinned = _pinned_buffer(total)
-    if arrays:
-        n = len(arrays)
-        src = np.fromiter((a.ctypes.data for a in arrays), dtype=np.uint64, count=n)
-        nbytes = np.fromiter((a.nbytes for a in arrays), dtype=np.uint64, count=n)
-        dst = np.empty(n, dtype=np.uint64)
-        dst[0::2] = pubs["obs_offset"]
-        dst[1::2] = pubs["qpd_offset"]
-        check(
-            _lib.load().qcut_gather_host(
-                _lib.np_ptr(src), _lib.np_ptr(nbytes), _lib.np_ptr(dst), n, pinned.data_ptr(), 0
-            ),
-            "qcut_gather_host",
-        )
+    gather_arrays(tables, arrays, pinned.data_ptr())
     data = torch.empty(total, dtype=torch.uint8, device="cuda")
     data.copy_(pinned[:total], non_blocking=True)
-    return DeviceBatch(tables, data, jit=jit)
+    return DeviceBatch(tables, data, flags=flags)

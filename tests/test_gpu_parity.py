@@ -1,0 +1,153 @@
+"""Parity tests proper (B200): the CUDA path, through the public API and the C ABI, against the oracle.
+
+Integer tallies must be bit-exact.  Expectation values are compared three ways:
+  * vs the oracle with E = tally/S ("exact"): the only differences allowed are fp64 summation-order
+    effects of K2, bounded here by 4 ulp of the largest partial sum -- in practice 0 ulp because K2
+    keeps the reference's order for C <= 1024;
+  * vs what the reference's own source produced (golden fixtures): within the reference's
+    self-noise from accumulating +-fl(1/S) shot by shot (1e-13 * kappa for S <= 4100);
+  * bit-identical to the reference when S is a power of two.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import _cases
+import _golden
+from oracle import oracle
+from qiskit_addon_cutting_b200 import (
+    BitArray, DataBin, PauliList, PrimitiveResult, PubResult, QuasiDistribution, SamplerResult, WeightType,
+    _lib, engine, reconstruct_expectation_values,
+)
+from qiskit_addon_cutting_b200.observable_grouping import ObservableCollection
+
+pytestmark = pytest.mark.gpu
+
+KAT = _golden.load_kat()
+
+
+def _hex(values):
+    return [float(v).hex() for v in values]
+
+
+def _device_tallies(results, coefficients, observables, flags=0):
+    if not isinstance(observables, dict):
+        observables, results = {"A": observables}, {"A": results}
+    labels = list(observables)
+    colls = [ObservableCollection(observables[label]) for label in labels]
+    coeffs = np.array([c for c, _ in coefficients], dtype=np.float64)
+    batch = engine.stage_v2([results[label] for label in labels], colls, coeffs, 0, len(coeffs),
+                            len(observables[labels[0]]), flags=flags)
+    batch.run()
+    torch.cuda.synchronize()
+    want = np.concatenate([t for label in labels for t in oracle.all_tallies(results, coefficients, observables)[label]])
+    return batch, batch.tallies.cpu().numpy()[: batch.tables.n_tallies], want
+
+
+def test_library_loaded_and_device_visible(lib):
+    assert lib.qcut_device_count() >= 1
+    assert torch.cuda.get_device_capability(0)[0] >= 10, "these kernels are built for sm_100a"
+
+
+def test_reference_v2_golden_vector(lib):
+    obs = BitArray(np.array([0, 0, 0, 1, 0, 0, 2, 3, 1, 0], dtype=np.uint8).reshape(-1, 1), 2)
+    qpd = BitArray(np.array([0, 1, 1, 3, 2, 0, 1, 3, 0, 2], dtype=np.uint8).reshape(-1, 1), 2)
+    results = PrimitiveResult([PubResult(DataBin(observable_measurements=obs, qpd_measurements=qpd))])
+    out = reconstruct_expectation_values(results, [(1.0, WeightType.EXACT)], PauliList(["II", "IZ", "ZI", "ZZ"]))
+    assert isinstance(out, list) and all(isinstance(v, np.float64) for v in out)
+    assert out == pytest.approx([0.0, -0.6, 0.0, -0.2])
+
+
+def test_reference_v1_trivial_and_truth_table(lib):
+    results = SamplerResult(quasi_dists=[QuasiDistribution({"0": 1.0})], metadata=[{}])
+    assert reconstruct_expectation_values(results, [(1.0, WeightType.EXACT)], PauliList(["ZZ"])) == [1.0]
+    # _process_outcome truth table (cog XZ: IZ, XI, XZ) through the V1 kernel: one outcome of weight 1
+    for outcome, expected in KAT["process_outcome"]["table"].items():
+        for key in (outcome, f"0b{outcome}", int(outcome, 2), hex(int(outcome, 2))):
+            results = SamplerResult(quasi_dists=[{key: 1.0}])
+            got = reconstruct_expectation_values(results, [(1.0, WeightType.EXACT)], PauliList(["IZ", "XI", "XZ"]))
+            assert got == expected, (key, got)
+
+
+def test_v1_case_bit_identical_to_reference(lib):
+    case = _golden.load_v1_case()
+    out = reconstruct_expectation_values(case["results"], case["coefficients"], case["observables"])
+    assert _hex(out) == _hex(case["reference_expvals"])
+
+
+@pytest.mark.parametrize("flags", [0, _lib.PLAN_NO_JIT, _lib.PLAN_GENERIC_ONLY], ids=["jit", "sliced_rt", "generic"])
+@pytest.mark.parametrize("name", _golden.CASE_NAMES)
+def test_tallies_bit_exact_on_golden_cases(lib, name, flags):
+    case = _golden.load_case(name)
+    batch, got, want = _device_tallies(case["results"], case["coefficients"], case["observables"], flags)
+    assert np.array_equal(got, want)
+    kernels = set(batch.plan.kernels())
+    if flags == _lib.PLAN_GENERIC_ONLY:
+        assert kernels == {0}
+    if flags == _lib.PLAN_NO_JIT:
+        assert max(kernels) <= 1
+
+
+@pytest.mark.parametrize("name", _golden.CASE_NAMES)
+def test_expvals_on_golden_cases(lib, name):
+    case = _golden.load_case(name)
+    out = np.array(reconstruct_expectation_values(case["results"], case["coefficients"], case["observables"]))
+    kappa = max(1.0, sum(abs(c) for c, _ in case["coefficients"]))
+    exact = np.array(oracle.reconstruct_exact(case["results"], case["coefficients"], case["observables"]))
+    assert np.max(np.abs(out - exact)) <= 4 * np.finfo(np.float64).eps * kappa
+    assert _hex(out) == _hex(exact), "K2 keeps the reference's summation order for C <= 1024"
+    assert np.max(np.abs(out - np.array(case["reference_expvals"]))) <= 1e-13 * kappa
+    if name == "pow2":
+        assert _hex(out) == _hex(case["reference_expvals"])
+
+
+@pytest.mark.parametrize("nbits,qbits", [(3, 1), (8, 8), (9, 2), (16, 1), (17, 3), (24, 9), (31, 1), (33, 4),
+                                          (47, 1), (56, 8), (64, 1), (65, 2), (100, 1), (127, 8), (200, 17)])
+@pytest.mark.parametrize("shots", [1, 100, 4096, 5000])
+def test_tallies_every_row_width(lib, nbits, qbits, shots):
+    """Row widths 1..25 bytes (bit-sliced and generic kernels), qpd widths 1..3 bytes, ragged shot counts."""
+    rng = np.random.default_rng(nbits * 7919 + shots)
+    observables = {"A": _cases.random_paulis(rng, 20, nbits, 1, min(nbits, 40), "Z")}
+    results = _cases.make_results(observables, 2, shots, qbits, seed=int(rng.integers(1 << 30)))
+    _, got, want = _device_tallies(results, [(0.5, WeightType.EXACT), (-0.5, WeightType.EXACT)], observables)
+    assert np.array_equal(got, want)
+
+
+def test_empty_pubs_and_zero_shots(lib):
+    """A PUB with zero shots contributes E = 0 (the reference's shot loop does not execute)."""
+    observables = {"A": PauliList(["ZI", "IZ"]), "B": PauliList(["II", "ZZ"])}
+    rng = np.random.default_rng(5)
+
+    def pub(shots, bits):
+        return PubResult(DataBin(observable_measurements=BitArray(_cases.random_bits(rng, shots, bits), bits),
+                                 qpd_measurements=BitArray(_cases.random_bits(rng, shots, 2), 2)))
+
+    results = {"A": PrimitiveResult([pub(0, 2), pub(7, 2)]), "B": PrimitiveResult([pub(5, 2), pub(0, 2)])}
+    coefficients = [(0.75, WeightType.EXACT), (-0.25, WeightType.EXACT)]
+    out = reconstruct_expectation_values(results, coefficients, observables)
+    assert _hex(out) == _hex(oracle.reconstruct_exact(results, coefficients, observables))
+    assert _hex(out) == _hex(oracle.reconstruct_literal(results, coefficients, observables)) or np.allclose(
+        out, oracle.reconstruct_literal(results, coefficients, observables), atol=1e-15)
+
+
+def test_many_terms_group_uses_specialised_kernel_and_matches(lib):
+    """cfg4 / cfg3 shapes at small size: > 12 terms on 8-byte rows -> NVRTC-specialised kernel."""
+    for name in ("heavy_hex", "wide_dense"):
+        results, coefficients, observables = _cases.SMALL_CASES[name]()
+        batch, got, want = _device_tallies(results, coefficients, observables)
+        assert max(batch.plan.kernels()) >= _lib.KERNEL_JIT0
+        assert "struct Terms" in batch.plan.source(_lib.KERNEL_JIT0)
+        assert np.array_equal(got, want)
+
+
+def test_large_chunked_reduction_matches_oracle(lib):
+    """C > 1024 coefficient tuples: K2 runs several chunks; result within summation-order noise of the oracle."""
+    rng = np.random.default_rng(77)
+    observables = {"A": _cases.random_paulis(rng, 5, 8, 1, 4, "Z"), "B": _cases.random_paulis(rng, 5, 6, 1, 4, "Z")}
+    C = 2500
+    coefficients = _cases.random_coefficients(rng, C, kappa=81.0)
+    results = _cases.make_results(observables, C, 64, 2, seed=78)
+    out = np.array(reconstruct_expectation_values(results, coefficients, observables))
+    want = np.array(oracle.reconstruct_exact(results, coefficients, observables))
+    assert np.max(np.abs(out - want)) <= 1e-12

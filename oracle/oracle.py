@@ -254,7 +254,10 @@ def reconstruct_exact(results, coefficients, observables) -> list:
     """Same loop nest with per-PUB ``E = tally / shots`` (one correctly rounded division)."""
 
     def pub_fn(obs_array, qpd_array, masks):
-        return tally_exact(obs_array, qpd_array, masks) / qpd_array.shape[0]
+        shots = qpd_array.shape[0]
+        if shots == 0:  # the reference's shot loop does not execute: expectation values stay 0
+            return np.zeros(len(masks))
+        return tally_exact(obs_array, qpd_array, masks) / shots
 
     return _reconstruct(results, coefficients, observables, pub_fn, _v1_literal)
 

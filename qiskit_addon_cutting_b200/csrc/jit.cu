@@ -101,7 +101,7 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
         "  for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {\n"
         "    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;\n"
         "    uint32_t a[G::BLOCKS][32]; uint32_t qp[G::BATCHES];\n"
-        "    qcut_step<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);\n"
+        "    qcut_step_any<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);\n"
         "    for (int u = 0; u < G::BATCHES; ++u) {\n"
         "      for (int blk = 0; blk < G::BLOCKS; ++blk)\n"
         "        for (int i = 0; i < G::PLANES; ++i) planes[(blk * 32 + i) * 32 + lane] = a[blk][u * G::PLANES + i];\n"

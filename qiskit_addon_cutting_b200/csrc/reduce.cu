@@ -7,35 +7,43 @@
 //         expvals += coeff[0] * current
 //
 // fp64 gather-product + segmented sum; no tensor cores (this is not a dense contraction).
-// Thread <-> observable k.  The sum over i keeps the reference's order: strictly ascending i
-// inside chunks of kReduceChunk tuples (separate multiply and add, no FMA contraction), chunks
-// combined in ascending order by a second launch.  For n_coeffs <= kReduceChunk the summation
-// order is therefore *identical* to the reference's; in every case it is deterministic.
+// A CTA owns kReduceChunk consecutive coefficient tuples x kReduceObs observables:
+//   phase 1 (all threads, latency hidden by parallelism): term[k][i] = coeff[i] * prod_label mean(...)
+//            -> shared memory;
+//   phase 2 (one thread per observable): sums its row in strictly ascending i, separate multiply and
+//            add, no FMA contraction -- the reference's order and rounding.
+// Chunks are combined in ascending order by a second launch.  For n_coeffs <= kReduceChunk the
+// summation order is therefore *identical* to the reference's; in every case it is deterministic.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qcut {
 
 constexpr int kReduceChunk = 1024;
-constexpr int kReduceThreads = 128;
+constexpr int kReduceObs = 8;
+constexpr int kReduceThreads = 256;
+constexpr int kReduceRow = kReduceChunk + 2;  // padded row (doubles) so the 8 rows start in different banks
 
 template <typename TallyT>
 __device__ __forceinline__ double pub_expval(const TallyT* __restrict__ tallies,
-                                             const qcut_pub_desc& pub, uint32_t term);
+                                             const qcut_pub_desc* __restrict__ pub, uint32_t term);
 
 // V2: exact int64 tally -> one correctly rounded division.  A PUB with zero shots contributes
 // 0.0, as the reference's empty shot loop does (cutting_reconstruction.py:155-161).
 template <>
 __device__ __forceinline__ double pub_expval<int64_t>(const int64_t* __restrict__ tallies,
-                                                      const qcut_pub_desc& pub, uint32_t term) {
-  if (pub.shots == 0) return 0.0;
-  return __ddiv_rn((double)__ldg(tallies + pub.tally_offset + term), (double)pub.shots);
+                                                      const qcut_pub_desc* __restrict__ pub, uint32_t term) {
+  const uint32_t shots = __ldg(&pub->shots);
+  if (shots == 0) return 0.0;
+  return __ddiv_rn((double)__ldg(tallies + __ldg(&pub->tally_offset) + term), (double)shots);
 }
 
 // V1: the quasi-probability kernel already produced fp64 expectation values.
 template <>
 __device__ __forceinline__ double pub_expval<double>(const double* __restrict__ expvals,
-                                                     const qcut_pub_desc& pub, uint32_t term) {
-  return __ldg(expvals + pub.tally_offset + term);
+                                                     const qcut_pub_desc* __restrict__ pub, uint32_t term) {
+  return __ldg(expvals + __ldg(&pub->tally_offset) + term);
 }
 
 template <typename TallyT>
@@ -45,37 +53,48 @@ reduce_partial_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* _
                       const uint32_t* __restrict__ lookup_start, const qcut_slot* __restrict__ lookup,
                       const double* __restrict__ coeffs, int64_t n_coeffs, int n_obs,
                       double* __restrict__ partial) {
-  const int k = blockIdx.x * kReduceThreads + threadIdx.x;
-  if (k >= n_obs) return;
+  extern __shared__ double s_term[];  // [kReduceObs][kReduceRow]
+  const int k_local = threadIdx.x % kReduceObs;
+  const int i_local = threadIdx.x / kReduceObs;
+  const int k = blockIdx.x * kReduceObs + k_local;
   const int64_t i0 = (int64_t)blockIdx.y * kReduceChunk;
-  const int64_t i1 = min(n_coeffs, i0 + kReduceChunk);
+  const int n_i = (int)min((int64_t)kReduceChunk, n_coeffs - i0);
 
-  double sum = 0.0;
-  for (int64_t i = i0; i < i1; ++i) {
-    double prod = 1.0;
-    for (int l = 0; l < n_labels; ++l) {
-      const qcut_label_desc lab = labels[l];
-      const uint32_t e0 = __ldg(lookup_start + lab.lookup_base + k);
-      const uint32_t e1 = __ldg(lookup_start + lab.lookup_base + k + 1);
-      double acc = 0.0;
-      for (uint32_t e = e0; e < e1; ++e) {
-        const qcut_slot slot = lookup[e];
-        const qcut_pub_desc pub = pubs[lab.pub_base + (uint64_t)i * lab.num_groups + slot.group];
-        acc = __dadd_rn(acc, pub_expval<TallyT>(tallies, pub, slot.term));
+  if (k < n_obs) {
+    for (int ii = i_local; ii < n_i; ii += kReduceThreads / kReduceObs) {
+      const int64_t i = i0 + ii;
+      double prod = 1.0;
+      for (int l = 0; l < n_labels; ++l) {
+        const qcut_label_desc lab = labels[l];
+        const uint32_t e0 = __ldg(lookup_start + lab.lookup_base + k);
+        const uint32_t e1 = __ldg(lookup_start + lab.lookup_base + k + 1);
+        double acc = 0.0;
+        for (uint32_t e = e0; e < e1; ++e) {
+          const qcut_slot slot = lookup[e];
+          acc = __dadd_rn(acc, pub_expval<TallyT>(tallies, pubs + lab.pub_base + (uint64_t)i * lab.num_groups + slot.group, slot.term));
+        }
+        // np.mean of the slot list: sum / n (exactly the value itself for the usual n == 1).
+        prod = __dmul_rn(prod, __ddiv_rn(acc, (double)(e1 - e0)));
       }
-      // np.mean of the slot list: sum / n (exactly the value itself for the usual n == 1).
-      const double mean = __ddiv_rn(acc, (double)(e1 - e0));
-      prod = __dmul_rn(prod, mean);
+      s_term[k_local * kReduceRow + ii] = __dmul_rn(__ldg(coeffs + i), prod);
     }
-    sum = __dadd_rn(sum, __dmul_rn(__ldg(coeffs + i), prod));
   }
-  partial[(int64_t)blockIdx.y * n_obs + k] = sum;
+  __syncthreads();
+  if (threadIdx.x < kReduceObs) {
+    const int kk = blockIdx.x * kReduceObs + threadIdx.x;
+    if (kk < n_obs) {
+      const double* __restrict__ row = s_term + threadIdx.x * kReduceRow;
+      double sum = 0.0;
+      for (int ii = 0; ii < n_i; ++ii) sum = __dadd_rn(sum, row[ii]);
+      partial[(int64_t)blockIdx.y * n_obs + kk] = sum;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(kReduceThreads)
+__global__ void __launch_bounds__(128)
 reduce_combine_kernel(const double* __restrict__ partial, int64_t n_chunks, int n_obs,
                       double* __restrict__ out) {
-  const int k = blockIdx.x * kReduceThreads + threadIdx.x;
+  const int k = blockIdx.x * 128 + threadIdx.x;
   if (k >= n_obs) return;
   double sum = 0.0;
   for (int64_t c = 0; c < n_chunks; ++c) sum = __dadd_rn(sum, partial[c * n_obs + k]);
@@ -97,13 +116,19 @@ int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qc
     set_error("qcut_reduce_launch: more than 65535 * 1024 coefficients per rank are not supported");
     return QCUT_ERR_INVALID;
   }
+  static bool configured[2] = {false, false};
+  const size_t smem = sizeof(double) * kReduceObs * kReduceRow;  // 64 KB + padding
+  const int which = sizeof(TallyT) == sizeof(int64_t) && std::is_same<TallyT, int64_t>::value ? 0 : 1;
+  if (!configured[which]) {
+    QCUT_CUDA(cudaFuncSetAttribute(reduce_partial_kernel<TallyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[which] = true;
+  }
   double* partial = static_cast<double*>(d_workspace);
-  const dim3 grid((n_obs + kReduceThreads - 1) / kReduceThreads, (unsigned)chunks);
-  reduce_partial_kernel<TallyT><<<grid, kReduceThreads, 0, stream>>>(
-      d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs,
-      partial);
+  const dim3 grid((n_obs + kReduceObs - 1) / kReduceObs, (unsigned)chunks);
+  reduce_partial_kernel<TallyT><<<grid, kReduceThreads, smem, stream>>>(
+      d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, partial);
   QCUT_CUDA(cudaGetLastError());
-  reduce_combine_kernel<<<grid.x, kReduceThreads, 0, stream>>>(partial, chunks, n_obs, d_out);
+  reduce_combine_kernel<<<(n_obs + 127) / 128, 128, 0, stream>>>(partial, chunks, n_obs, d_out);
   QCUT_CUDA(cudaGetLastError());
   return QCUT_OK;
 }

@@ -160,18 +160,20 @@ QCUT_DEV void qcut_qp_slow(const uint8_t* __restrict__ qpd_s, int nbq, int n, in
 //   a[blk][.]  <- bit-planes of the observable rows of this lane's shots,
 //   qp[u]      <- bit j = parity of ALL bits of the qpd row of the shot in row j, batch u
 //                 (reference cutting_reconstruction.py:213: pad bits above num_bits count too).
-// Rows past the end of the PUB are forced to zero (they then count as "even" and are removed
-// again by tally = n - 2 * odd).
-template <int NB>
+// FULL = true: the step holds exactly STEP_SHOTS shots -- no predication, every load is
+// "lane base + immediate".  FULL = false (last step of a PUB): loads are predicated and rows past
+// the end of the PUB are forced to zero (they then count as "even" and are removed again by
+// tally = n - 2 * odd).
+template <int NB, bool FULL>
 QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __restrict__ qpd_s, int nbq, int n,
                         int lane, uint32_t (*a)[32], uint32_t* qp) {
   typedef QcutGeo<NB> G;
   // ---- coalesced 128-bit loads of the observable rows ------------------------------------
+  const uint8_t* __restrict__ obs_l = obs_s + lane * 16;
 #pragma unroll
   for (int k = 0; k < G::CHUNKS; ++k) {
-    const int idx = k * 32 + lane;
     qcut_u4 v = {0u, 0u, 0u, 0u};
-    if (idx * G::SPC < n) v = qcut_ld16(obs_s + (uint64_t)idx * 16);
+    if (FULL || (k * 32 + lane) * G::SPC < n) v = qcut_ld16(obs_l + k * 512);
     if constexpr (NB == 8) {
       a[0][2 * k] = v.x; a[1][2 * k] = v.y;
       a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
@@ -189,11 +191,11 @@ QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __rest
   } else if constexpr (NB == 1) {
     // Same geometry as the observable rows: transpose the qpd block too, XOR its 8 planes.
     uint32_t q[32];
+    const uint8_t* __restrict__ qpd_l = qpd_s + lane * 16;
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
-      const int idx = k * 32 + lane;
       qcut_u4 v = {0u, 0u, 0u, 0u};
-      if (idx * G::SPC < n) v = qcut_ld16(qpd_s + (uint64_t)idx * 16);
+      if (FULL || (k * 32 + lane) * G::SPC < n) v = qcut_ld16(qpd_l + k * 512);
       q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
     }
     qcut_transpose32(q);
@@ -207,26 +209,27 @@ QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __rest
   } else {
     // One qpd byte per shot: fold each byte to its parity, then gather the parity bits of
     // four bytes with one multiply (no carries: all partial products hit distinct bits).
+    const uint8_t* __restrict__ qpd_l = qpd_s + lane * G::SPC;  // SPC qpd bytes per chunk per lane
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
       const int idx = k * 32 + lane;
       if constexpr (NB == 8) {
         if (k & 1) continue;  // chunks k, k+1 -> rows 2k .. 2k+3
         uint32_t w = 0;
-        if (idx * 2 < n) w = qcut_ld2(qpd_s + (uint64_t)idx * 2);
-        if ((idx + 32) * 2 < n) w |= qcut_ld2(qpd_s + (uint64_t)(idx + 32) * 2) << 16;
+        if (FULL || idx * 2 < n) w = qcut_ld2(qpd_l + k * 64);
+        if (FULL || (idx + 32) * 2 < n) w |= qcut_ld2(qpd_l + (k + 1) * 64) << 16;
         const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
         qp[0] |= nib << (2 * k);
       } else if constexpr (NB == 4) {
         uint32_t w = 0;
-        if (idx * 4 < n) w = qcut_ld4(qpd_s + (uint64_t)idx * 4);
+        if (FULL || idx * 4 < n) w = qcut_ld4(qpd_l + k * 128);
         const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
         qp[0] |= nib << (4 * k);
       } else {  // NB == 2: bytes (b0, b2) of each word -> batch 0, (b1, b3) -> batch 1
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t w = 0;
-          if (idx * 8 + 4 * h < n) w = qcut_ld4(qpd_s + (uint64_t)idx * 8 + 4 * h);
+          if (FULL || idx * 8 + 4 * h < n) w = qcut_ld4(qpd_l + k * 256 + 4 * h);
           const uint32_t r = (qcut_byte_parity(w) * 0x01100220u) >> 24;
           qp[0] |= (r & 3u) << (4 * k + 2 * h);
           qp[G::BATCHES - 1] |= ((r >> 4) & 3u) << (4 * k + 2 * h);
@@ -239,7 +242,7 @@ QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __rest
 #pragma unroll
   for (int blk = 0; blk < G::BLOCKS; ++blk) qcut_transpose32(a[blk]);
 
-  if (n != G::STEP_SHOTS) {
+  if constexpr (!FULL) {
     // Tail step: rows past the end of the PUB may hold bytes of the padding / next matrix.
 #pragma unroll
     for (int u = 0; u < G::BATCHES; ++u) {
@@ -255,6 +258,13 @@ QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __rest
   }
 }
 
+template <int NB>
+QCUT_DEV void qcut_step_any(const uint8_t* __restrict__ obs_s, const uint8_t* __restrict__ qpd_s, int nbq, int n,
+                            int lane, uint32_t (*a)[32], uint32_t* qp) {
+  if (n == QcutGeo<NB>::STEP_SHOTS) qcut_step<NB, true>(obs_s, qpd_s, nbq, n, lane, a, qp);
+  else qcut_step<NB, false>(obs_s, qpd_s, nbq, n, lane, a, qp);
+}
+
 // ---- term engine A: masks baked into generated code (struct Terms from jit.cu) -----------------
 // acc[] receives, packed four 8-bit fields per word, the number of odd-parity shots this lane
 // saw for every term (<= 128 per tile, so the fields cannot overflow).
@@ -268,7 +278,7 @@ QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __r
     const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
     uint32_t a[G::BLOCKS][32];
     uint32_t qp[G::BATCHES];
-    qcut_step<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
+    qcut_step_any<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
 #pragma unroll
     for (int u = 0; u < G::BATCHES; ++u)
       Terms::run(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], acc);
@@ -295,6 +305,12 @@ QCUT_DEV uint32_t qcut_rt_term(const uint32_t* planes, uint32_t qp, uint32_t m_l
 }
 
 #ifndef QCUT_HOST_EMU
+// 64-bit integer reduction to global memory.  Plain PTX: the lanes target distinct addresses, so the
+// compiler's warp-aggregated atomicAdd expansion (match + REDUX + elect) would only add instructions.
+QCUT_DEV void qcut_red_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
 // Warp-level flush of the packed per-lane counters: tally[t] += ns - 2 * (#odd shots).
 template <int T>
 QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long long* __restrict__ tally) {
@@ -307,7 +323,7 @@ QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long lo
     if (lane < 4 && t < T) {
       const uint32_t pair = (lane & 1) ? od : ev;
       const long long odd = (lane & 2) ? (pair >> 16) : (pair & 0xFFFFu);
-      atomicAdd(tally + t, (unsigned long long)((long long)ns - 2 * odd));
+      qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2 * odd));
     }
   }
 }

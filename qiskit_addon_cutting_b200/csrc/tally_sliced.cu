@@ -27,7 +27,7 @@ __device__ __forceinline__ void rt_tile(const uint8_t* __restrict__ obs, const u
     const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
     uint32_t a[G::BLOCKS][32];
     uint32_t qp[G::BATCHES];
-    qcut_step<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
+    qcut_step_any<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
 #pragma unroll
     for (int u = 0; u < G::BATCHES; ++u) {
       __syncwarp();

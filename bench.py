@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per baseline measurement")
+    ap.add_argument("--plan-flags", type=int, default=0, help="qcut_plan_create flags (experiments: 1 no JIT, 2 generic only, 4 staged)")
     return ap.parse_args()
 
 
@@ -198,7 +199,7 @@ def ours_arm(args):
     w = W.get_workload(args.workload, args.scale)
     tables = W.build_tables(w, rank, world)
     data = W.device_data(tables, w.seed * 1000 + rank)
-    batch = engine.DeviceBatch(tables, data)
+    batch = engine.DeviceBatch(tables, data, flags=args.plan_flags)
     out = batch.out[: tables.n_obs]
 
     def step():

@@ -103,6 +103,7 @@ int qcut_device_count(void);
  * flags: QCUT_PLAN_NO_JIT disables NVRTC specialisation, QCUT_PLAN_GENERIC_ONLY forces kernel 0. */
 #define QCUT_PLAN_NO_JIT 1u
 #define QCUT_PLAN_GENERIC_ONLY 2u
+#define QCUT_PLAN_STAGED 4u /* specialised kernels prefetch each step through shared memory with bulk async copies (UBLKCP + mbarrier) instead of loading straight from HBM; measured slower on B200 for this ALU-issue-bound kernel, kept for experiments */
 #define QCUT_MAX_JIT_KERNELS 8
 int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
                      size_t mask_bytes, unsigned flags, qcut_plan** out_plan);

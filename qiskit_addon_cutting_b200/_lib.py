@@ -22,6 +22,7 @@ MAX_OBS_BYTES = 64
 ABI_VERSION = 2
 PLAN_NO_JIT = 1
 PLAN_GENERIC_ONLY = 2
+PLAN_STAGED = 4
 KERNEL_GENERIC, KERNEL_SLICED_RT, KERNEL_JIT0 = 0, 1, 2
 
 

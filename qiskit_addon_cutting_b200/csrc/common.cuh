@@ -47,7 +47,11 @@ struct JitKernel {
   cudaLibrary_t library = nullptr;
   cudaKernel_t kernel = nullptr;
   int min_blocks = 2;
+  int threads = 256;
   int group = -1;  // representative group
+  int nb_obs = 0;
+  bool staged = true;  // bulk-copy staged stream (shared-memory prefetch) vs direct global loads
+  int smem_bytes = 0;
 };
 
 }  // namespace qcut

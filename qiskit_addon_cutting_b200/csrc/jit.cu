@@ -8,6 +8,7 @@
 // they are compiled concurrently and each streams its own tile list (api.cu).
 #include <nvrtc.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 #include <thread>
@@ -36,11 +37,13 @@ static std::string plane_name(uint32_t nb, uint32_t byte, uint32_t bit) {
 }
 
 // The translation unit for one group.  Pure host code.
-std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out) {
+std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out,
+                                   bool staged, int threads) {
   if (!jit_supports(gd)) return std::string();
   const uint32_t T = gd.n_terms, nb = gd.nb_obs;
   // Register budget: 32 per block + packed counters + ~28 of addressing / temporaries.
-  const int min_blocks = ((nb == 8 ? 64 : 32) + (int)((T + 3) / 4) + 28 > 128) ? 1 : 2;
+  int min_blocks = ((nb == 8 ? 64 : 32) + (int)((T + 3) / 4) + 28 > 128) ? 1 : 2;
+  if (min_blocks_out && *min_blocks_out > 0) min_blocks = *min_blocks_out;  // explicit override
   if (min_blocks_out) *min_blocks_out = min_blocks;
 
   std::ostringstream os;
@@ -64,26 +67,42 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   }
   os << "  }\n};\n\n";
   os << "#ifndef QCUT_HOST_EMU\n";
-  os << "extern \"C\" __global__ void __launch_bounds__(256, " << min_blocks << ")\n";
-  os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
-        "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
-        "                  unsigned long long* __restrict__ tallies) {\n"
-        "  const int lane = threadIdx.x & 31;\n"
-        "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
-        "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
-        "       tile += n_warps) {\n"
-        "    const QcutTile te = tiles[tile];\n"
-        "    const QcutPub pub = pubs[te.pub];\n"
-        "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
-        "    const int64_t left = (int64_t)pub.shots - shot0;\n"
-        "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
-        "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
-        "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
-        "    uint32_t acc[Terms::NACC];\n"
-        "    qcut_lane_tile<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n"
-        "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
-        "  }\n"
-        "}\n";
+  os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n";
+  if (staged) {
+    // Bulk-copy staged stream: one staging buffer + one mbarrier per warp in dynamic shared memory.
+    os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  extern __shared__ __align__(128) uint8_t qcut_smem[];\n"
+          "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n"
+          "  const int n_warps_cta = blockDim.x >> 5;\n"
+          "  uint8_t* stage = qcut_smem + (size_t)warp * QcutStage<Terms::NB>::BYTES;\n"
+          "  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(\n"
+          "      qcut_smem + (size_t)n_warps_cta * QcutStage<Terms::NB>::BYTES) + warp;\n"
+          "  qcut_warp_stream<Terms::NB, Terms>(data, pubs, tiles, n_tiles, (int64_t)blockIdx.x * n_warps_cta + warp,\n"
+          "                                     (int64_t)gridDim.x * n_warps_cta, tallies, stage, mbar, lane);\n"
+          "}\n";
+  } else {
+    os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  const int lane = threadIdx.x & 31;\n"
+          "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+          "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
+          "       tile += n_warps) {\n"
+          "    const QcutTile te = tiles[tile];\n"
+          "    const QcutPub pub = pubs[te.pub];\n"
+          "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+          "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+          "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
+          "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "    uint32_t acc[Terms::NACC];\n"
+          "    qcut_lane_tile<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n"
+          "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
+          "  }\n"
+          "}\n";
+  }
   os << "#else  // host emulation entry: one lane of one tile, unpacked odd counts\n";
   os << "extern \"C\" int qcut_emu_lane_tile(const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
         "                                  uint32_t* odd_out) {\n"
@@ -173,7 +192,15 @@ int jit_build(qcut_plan* plan) {
   std::vector<std::string> errors(n);
   auto work = [&](size_t i) {
     JitKernel& jk = plan->jit[i];
-    jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks);
+    jk.staged = (plan->flags & QCUT_PLAN_STAGED) != 0;
+    jk.nb_obs = (int)plan->groups[jk.group].nb_obs;
+    // tuning knobs (experiments only): QCUT_JIT_THREADS (CTA size), QCUT_JIT_MINBLOCKS (launch bound)
+    const char* env_threads = std::getenv("QCUT_JIT_THREADS");
+    const char* env_blocks = std::getenv("QCUT_JIT_MINBLOCKS");
+    jk.threads = env_threads ? std::atoi(env_threads) : 256;
+    if (jk.threads < 32 || jk.threads > 1024 || jk.threads % 32) jk.threads = 256;
+    jk.min_blocks = env_blocks ? std::atoi(env_blocks) : 0;
+    jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads);
     rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
   };
   std::vector<std::thread> pool;
@@ -189,6 +216,14 @@ int jit_build(qcut_plan* plan) {
     cudaError_t err = cudaLibraryLoadData(&jk.library, jk.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (err == cudaSuccess) err = cudaLibraryGetKernel(&jk.kernel, jk.library, "qcut_tally_sliced");
     if (err != cudaSuccess) return cuda_fail(err, "cudaLibraryLoadData(qcut_tally_sliced)");
+    if (jk.staged) {
+      // per warp: one step of observable rows + one step of qpd bytes, plus one mbarrier
+      const int stage = jk.nb_obs == 8 ? 9216 : jk.nb_obs == 4 ? 5120 : jk.nb_obs == 2 ? 6144 : 8192;
+      jk.smem_bytes = (jk.threads / 32) * (stage + 8);
+      int dev = 0;
+      QCUT_CUDA(cudaGetDevice(&dev));
+      QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));
+    }
     jk.cubin.clear();
     jk.cubin.shrink_to_fit();
   }
@@ -210,12 +245,14 @@ int launch_tally_jit(const JitKernel& jk, const uint8_t* d_data, const qcut_pub_
   }
   // Persistent grid: min_blocks CTAs of 8 warps per SM; warps stride over the tile list so that all
   // SMs sweep the PUB table together (DRAM pages and the instruction cache see one stream).
-  const int64_t want = (n_tiles + 7) / 8;
+  const int warps = jk.threads / 32;
+  const int64_t want = (n_tiles + warps - 1) / warps;
   const int64_t cap = (int64_t)sm_count() * jk.min_blocks;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   unsigned long long* tallies = reinterpret_cast<unsigned long long*>(d_tallies);
   void* args[] = {(void*)&d_data, (void*)&d_pubs, (void*)&d_tiles, (void*)&n_tiles, (void*)&tallies};
-  QCUT_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jk.kernel), dim3(grid), dim3(256), args, 0, stream));
+  QCUT_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jk.kernel), dim3(grid), dim3(jk.threads), args,
+                             (size_t)jk.smem_bytes, stream));
   return QCUT_OK;
 }
 
@@ -229,7 +266,7 @@ size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const
   if (!h_groups || group < 0 || group >= n_groups) return 0;
   const qcut_group_desc& gd = h_groups[group];
   if ((size_t)gd.mask_offset + (size_t)gd.n_terms * gd.nb_obs > mask_bytes) return 0;
-  const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr);
+  const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, true, 256);
   if (src.empty()) return 0;
   if (buf && buf_len) {
     const size_t n = src.size() < buf_len - 1 ? src.size() : buf_len - 1;

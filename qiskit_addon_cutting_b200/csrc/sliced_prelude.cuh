@@ -73,8 +73,58 @@ QCUT_DEV uint32_t qcut_ld2(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); ret
 QCUT_DEV uint32_t qcut_ld1(const uint8_t* p) { return *p; }
 #endif
 
+// ---- where a step's bytes come from -------------------------------------------------------------
+// QcutSrcGlobal: straight from HBM (coalesced LDG.128, L1 no-allocate).
+// QcutSrcShared: from the warp's staging buffer in shared memory, filled ahead of time by a bulk
+//                asynchronous copy (cp.async.bulk -> UBLKCP, completion on an mbarrier), so the
+//                HBM latency of step s+1 is hidden behind the arithmetic of step s.
+// Offsets are bytes relative to the first observable / qpd byte of the step.
+struct QcutSrcGlobal {
+  const uint8_t* obs;
+  const uint8_t* qpd;
+  QCUT_MDEV qcut_u4 obs16(int off) const { return qcut_ld16(obs + off); }
+  QCUT_MDEV qcut_u4 qpd16(int off) const { return qcut_ld16(qpd + off); }
+  QCUT_MDEV uint32_t qpd4(int off) const { return qcut_ld4(qpd + off); }
+  QCUT_MDEV uint32_t qpd2(int off) const { return qcut_ld2(qpd + off); }
+};
+
+#ifndef QCUT_HOST_EMU
+struct QcutSrcShared {
+  uint32_t obs;  // shared-window addresses
+  uint32_t qpd;
+  QCUT_MDEV qcut_u4 obs16(int off) const {
+    qcut_u4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(obs + off));
+    return v;
+  }
+  QCUT_MDEV qcut_u4 qpd16(int off) const {
+    qcut_u4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(qpd + off));
+    return v;
+  }
+  QCUT_MDEV uint32_t qpd4(int off) const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(qpd + off));
+    return v;
+  }
+  QCUT_MDEV uint32_t qpd2(int off) const {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(qpd + off));
+    return v;
+  }
+};
+#else
+typedef QcutSrcGlobal QcutSrcShared;  // the harness copies the step's bytes into a host buffer first
+#endif
+
+// Logical right shift by a constant on the FMA pipe (IMAD.HI) instead of the ALU pipe (SHF): the
+// kernels are bound by ALU-pipe issue (LOP3 / PRMT), while the FMA pipe is nearly idle.
+template <int S>
+QCUT_DEV uint32_t qcut_shr(uint32_t x) { return __umulhi(x, 1u << (32 - S)); }
+
 // In-register 32x32 bit-matrix transposition: afterwards bit r of a[i] is bit i of the old a[r].
-// Two byte-granular stages are single PRMTs; the three bit-granular stages are shift + LOP3 selects.
+// Two byte-granular stages are single PRMTs; the three bit-granular stages are one LOP3 select per
+// output word with both shifts on the FMA pipe (IMAD.SHL / IMAD.HI).
 QCUT_DEV void qcut_transpose32(uint32_t* a) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -94,29 +144,29 @@ QCUT_DEV void qcut_transpose32(uint32_t* a) {
     if (j & 4) continue;
     const uint32_t x = a[j], y = a[j + 4];
     a[j] = (x & 0x0F0F0F0Fu) | ((y << 4) & 0xF0F0F0F0u);
-    a[j + 4] = ((x >> 4) & 0x0F0F0F0Fu) | (y & 0xF0F0F0F0u);
+    a[j + 4] = (qcut_shr<4>(x) & 0x0F0F0F0Fu) | (y & 0xF0F0F0F0u);
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j & 2) continue;
     const uint32_t x = a[j], y = a[j + 2];
     a[j] = (x & 0x33333333u) | ((y << 2) & 0xCCCCCCCCu);
-    a[j + 2] = ((x >> 2) & 0x33333333u) | (y & 0xCCCCCCCCu);
+    a[j + 2] = (qcut_shr<2>(x) & 0x33333333u) | (y & 0xCCCCCCCCu);
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j & 1) continue;
     const uint32_t x = a[j], y = a[j + 1];
     a[j] = (x & 0x55555555u) | ((y << 1) & 0xAAAAAAAAu);
-    a[j + 1] = ((x >> 1) & 0x55555555u) | (y & 0xAAAAAAAAu);
+    a[j + 1] = (qcut_shr<1>(x) & 0x55555555u) | (y & 0xAAAAAAAAu);
   }
 }
 
 // Parity of each byte of v, delivered at bit 0 of that byte.
 QCUT_DEV uint32_t qcut_byte_parity(uint32_t v) {
-  v ^= v >> 4;
-  v ^= v >> 2;
-  v ^= v >> 1;
+  v ^= qcut_shr<4>(v);
+  v ^= qcut_shr<2>(v);
+  v ^= qcut_shr<1>(v);
   return v & 0x01010101u;
 }
 
@@ -129,6 +179,7 @@ struct QcutGeo {
   static const int RPC = (NB == 8) ? 2 : 4;           // rows per chunk (per block)
   static const int STEP_SHOTS = CHUNKS * 32 * SPC;
   static const int PLANES = 32 / BATCHES;             // registers per batch in one block
+  static const int QRAW = (NB == 1) ? 32 : (NB == 2) ? 16 : 8;  // raw qpd words per lane per step
 };
 
 // Shot (relative to the step) held by row j, sub-shot u of this lane.
@@ -156,24 +207,20 @@ QCUT_DEV void qcut_qp_slow(const uint8_t* __restrict__ qpd_s, int nbq, int n, in
   }
 }
 
-// One step (n <= STEP_SHOTS shots starting at obs_s / qpd_s) for one lane:
-//   a[blk][.]  <- bit-planes of the observable rows of this lane's shots,
-//   qp[u]      <- bit j = parity of ALL bits of the qpd row of the shot in row j, batch u
-//                 (reference cutting_reconstruction.py:213: pad bits above num_bits count too).
+// ---- the pieces of one step (n <= STEP_SHOTS shots) for one lane ------------------------------------
 // FULL = true: the step holds exactly STEP_SHOTS shots -- no predication, every load is
 // "lane base + immediate".  FULL = false (last step of a PUB): loads are predicated and rows past
-// the end of the PUB are forced to zero (they then count as "even" and are removed again by
-// tally = n - 2 * odd).
-template <int NB, bool FULL>
-QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __restrict__ qpd_s, int nbq, int n,
-                        int lane, uint32_t (*a)[32], uint32_t* qp) {
+// the end of the PUB are forced to zero afterwards (qcut_mask_tail); they then count as "even" and
+// are removed again by tally = n - 2 * odd.
+
+// (1) coalesced 128-bit loads of the observable rows into the row registers a[blk][j]
+template <int NB, bool FULL, class Src>
+QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32]) {
   typedef QcutGeo<NB> G;
-  // ---- coalesced 128-bit loads of the observable rows ------------------------------------
-  const uint8_t* __restrict__ obs_l = obs_s + lane * 16;
 #pragma unroll
   for (int k = 0; k < G::CHUNKS; ++k) {
     qcut_u4 v = {0u, 0u, 0u, 0u};
-    if (FULL || (k * 32 + lane) * G::SPC < n) v = qcut_ld16(obs_l + k * 512);
+    if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
     if constexpr (NB == 8) {
       a[0][2 * k] = v.x; a[1][2 * k] = v.y;
       a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
@@ -181,88 +228,134 @@ QCUT_DEV void qcut_step(const uint8_t* __restrict__ obs_s, const uint8_t* __rest
       a[0][4 * k] = v.x; a[0][4 * k + 1] = v.y; a[0][4 * k + 2] = v.z; a[0][4 * k + 3] = v.w;
     }
   }
+}
 
-  // ---- qpd parity plane(s) -----------------------------------------------------------------
-#pragma unroll
-  for (int u = 0; u < G::BATCHES; ++u) qp[u] = 0;
-  if (nbq != 1) {
-    // Any other qpd row width: per-shot byte loop (rare: more than 8 cut measurements).
-    qcut_qp_slow<NB>(qpd_s, nbq, n, lane, qp);
-  } else if constexpr (NB == 1) {
-    // Same geometry as the observable rows: transpose the qpd block too, XOR its 8 planes.
-    uint32_t q[32];
-    const uint8_t* __restrict__ qpd_l = qpd_s + lane * 16;
+// (2) raw qpd bytes (one byte per shot) of this lane's shots, QRAW words in row order:
+//     NB = 8: word m = qpd bytes of rows 4m..4m+3;  NB = 4: word k = rows 4k..4k+3;
+//     NB = 2: word 2k+h = bytes (row 4k+2h, batch 0/1), (row 4k+2h+1, batch 0/1);
+//     NB = 1: the 32 words of the qpd block, same geometry as the observable block.
+template <int NB, bool FULL, class Src>
+QCUT_DEV void qcut_qpd_loads(const Src src, int n, int lane, uint32_t* qraw) {
+  typedef QcutGeo<NB> G;
+  if constexpr (NB == 1) {
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
       qcut_u4 v = {0u, 0u, 0u, 0u};
-      if (FULL || (k * 32 + lane) * G::SPC < n) v = qcut_ld16(qpd_l + k * 512);
-      q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
-    }
-    qcut_transpose32(q);
-#pragma unroll
-    for (int u = 0; u < G::BATCHES; ++u) {
-      uint32_t x = 0;
-#pragma unroll
-      for (int b = 0; b < G::PLANES; ++b) x ^= q[u * G::PLANES + b];
-      qp[u] = x;
+      if (FULL || (k * 32 + lane) * G::SPC < n) v = src.qpd16(lane * 16 + k * 512);
+      qraw[4 * k] = v.x; qraw[4 * k + 1] = v.y; qraw[4 * k + 2] = v.z; qraw[4 * k + 3] = v.w;
     }
   } else {
-    // One qpd byte per shot: fold each byte to its parity, then gather the parity bits of
-    // four bytes with one multiply (no carries: all partial products hit distinct bits).
-    const uint8_t* __restrict__ qpd_l = qpd_s + lane * G::SPC;  // SPC qpd bytes per chunk per lane
+    const int ql = lane * G::SPC;  // SPC qpd bytes per chunk per lane
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
       const int idx = k * 32 + lane;
       if constexpr (NB == 8) {
         if (k & 1) continue;  // chunks k, k+1 -> rows 2k .. 2k+3
         uint32_t w = 0;
-        if (FULL || idx * 2 < n) w = qcut_ld2(qpd_l + k * 64);
-        if (FULL || (idx + 32) * 2 < n) w |= qcut_ld2(qpd_l + (k + 1) * 64) << 16;
-        const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
-        qp[0] |= nib << (2 * k);
+        if (FULL || idx * 2 < n) w = src.qpd2(ql + k * 64);
+        if (FULL || (idx + 32) * 2 < n) w |= src.qpd2(ql + (k + 1) * 64) << 16;
+        qraw[k / 2] = w;
       } else if constexpr (NB == 4) {
         uint32_t w = 0;
-        if (FULL || idx * 4 < n) w = qcut_ld4(qpd_l + k * 128);
-        const uint32_t nib = (qcut_byte_parity(w) * 0x01020408u) >> 24;
-        qp[0] |= nib << (4 * k);
-      } else {  // NB == 2: bytes (b0, b2) of each word -> batch 0, (b1, b3) -> batch 1
+        if (FULL || idx * 4 < n) w = src.qpd4(ql + k * 128);
+        qraw[k] = w;
+      } else {  // NB == 2
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t w = 0;
-          if (FULL || idx * 8 + 4 * h < n) w = qcut_ld4(qpd_l + k * 256 + 4 * h);
-          const uint32_t r = (qcut_byte_parity(w) * 0x01100220u) >> 24;
-          qp[0] |= (r & 3u) << (4 * k + 2 * h);
-          qp[G::BATCHES - 1] |= ((r >> 4) & 3u) << (4 * k + 2 * h);
+          if (FULL || idx * 8 + 4 * h < n) w = src.qpd4(ql + k * 256 + 4 * h);
+          qraw[2 * k + h] = w;
         }
       }
     }
   }
+}
 
-  // ---- bit-slice ---------------------------------------------------------------------------
-#pragma unroll
-  for (int blk = 0; blk < G::BLOCKS; ++blk) qcut_transpose32(a[blk]);
-
-  if constexpr (!FULL) {
-    // Tail step: rows past the end of the PUB may hold bytes of the padding / next matrix.
+// (3) qpd parity plane(s): bit j of qp[u] = parity of ALL bits of the qpd row of the shot in row j,
+//     batch u (reference cutting_reconstruction.py:213: pad bits above num_bits count too).
+template <int NB>
+QCUT_DEV void qcut_qpd_planes(uint32_t* qraw, uint32_t* qp) {
+  typedef QcutGeo<NB> G;
+  if constexpr (NB == 1) {
+    // Same geometry as the observable rows: transpose the qpd block too, XOR its 8 planes per batch.
+    qcut_transpose32(qraw);
 #pragma unroll
     for (int u = 0; u < G::BATCHES; ++u) {
-      uint32_t valid = 0;
+      uint32_t x = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) valid |= (uint32_t)(qcut_shot_of<NB>(j, u, lane) < n) << j;
-      qp[u] &= valid;
+      for (int b = 0; b < G::PLANES; ++b) x ^= qraw[u * G::PLANES + b];
+      qp[u] = x;
+    }
+  } else {
+    // Fold each byte to its parity, then gather the parity bits of four bytes with one multiply
+    // (no carries: all partial products hit distinct bits).
 #pragma unroll
-      for (int blk = 0; blk < G::BLOCKS; ++blk)
+    for (int u = 0; u < G::BATCHES; ++u) qp[u] = 0;
 #pragma unroll
-        for (int b = 0; b < G::PLANES; ++b) a[blk][u * G::PLANES + b] &= valid;
+    for (int i = 0; i < G::QRAW; ++i) {
+      if constexpr (NB == 2) {  // bytes (b0, b2) of each word -> batch 0, (b1, b3) -> batch 1
+        const uint32_t r = (qcut_byte_parity(qraw[i]) * 0x01100220u) >> 24;
+        qp[0] |= (r & 3u) << (2 * i);
+        qp[G::BATCHES - 1] |= ((r >> 4) & 3u) << (2 * i);
+      } else {
+        const uint32_t nib = (qcut_byte_parity(qraw[i]) * 0x01020408u) >> 24;
+        qp[0] |= nib << (4 * i);
+      }
     }
   }
+}
+
+// (4) tail step: rows past the end of the PUB may hold bytes of the padding / next matrix.
+template <int NB>
+QCUT_DEV void qcut_mask_tail(int n, int lane, uint32_t (*a)[32], uint32_t* qp) {
+  typedef QcutGeo<NB> G;
+#pragma unroll
+  for (int u = 0; u < G::BATCHES; ++u) {
+    uint32_t valid = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) valid |= (uint32_t)(qcut_shot_of<NB>(j, u, lane) < n) << j;
+    qp[u] &= valid;
+#pragma unroll
+    for (int blk = 0; blk < G::BLOCKS; ++blk)
+#pragma unroll
+      for (int b = 0; b < G::PLANES; ++b) a[blk][u * G::PLANES + b] &= valid;
+  }
+}
+
+// The whole step: a[blk][.] <- bit-planes of this lane's shots, qp[u] <- qpd parity plane(s).
+// qpd_g always points at the step's qpd rows in global memory (used for qpd rows wider than one byte).
+template <int NB, bool FULL, class Src>
+QCUT_DEV void qcut_step(const Src src, const uint8_t* __restrict__ qpd_g, int nbq, int n, int lane,
+                        uint32_t (*a)[32], uint32_t* qp) {
+  typedef QcutGeo<NB> G;
+  qcut_step_loads<NB, FULL, Src>(src, n, lane, a);
+  if (nbq == 1) {
+    uint32_t qraw[G::QRAW];
+    qcut_qpd_loads<NB, FULL, Src>(src, n, lane, qraw);
+    qcut_qpd_planes<NB>(qraw, qp);
+  } else {
+    // Any other qpd row width: per-shot byte loop (rare: more than 8 cut measurements).
+#pragma unroll
+    for (int u = 0; u < G::BATCHES; ++u) qp[u] = 0;
+    qcut_qp_slow<NB>(qpd_g, nbq, n, lane, qp);
+  }
+#pragma unroll
+  for (int blk = 0; blk < G::BLOCKS; ++blk) qcut_transpose32(a[blk]);
+  if constexpr (!FULL) qcut_mask_tail<NB>(n, lane, a, qp);
+}
+
+template <int NB, class Src>
+QCUT_DEV void qcut_step_src(const Src src, const uint8_t* __restrict__ qpd_g, int nbq, int n, int lane,
+                            uint32_t (*a)[32], uint32_t* qp) {
+  if (n == QcutGeo<NB>::STEP_SHOTS) qcut_step<NB, true, Src>(src, qpd_g, nbq, n, lane, a, qp);
+  else qcut_step<NB, false, Src>(src, qpd_g, nbq, n, lane, a, qp);
 }
 
 template <int NB>
 QCUT_DEV void qcut_step_any(const uint8_t* __restrict__ obs_s, const uint8_t* __restrict__ qpd_s, int nbq, int n,
                             int lane, uint32_t (*a)[32], uint32_t* qp) {
-  if (n == QcutGeo<NB>::STEP_SHOTS) qcut_step<NB, true>(obs_s, qpd_s, nbq, n, lane, a, qp);
-  else qcut_step<NB, false>(obs_s, qpd_s, nbq, n, lane, a, qp);
+  const QcutSrcGlobal src = {obs_s, qpd_s};
+  qcut_step_src<NB, QcutSrcGlobal>(src, qpd_s, nbq, n, lane, a, qp);
 }
 
 // ---- term engine A: masks baked into generated code (struct Terms from jit.cu) -----------------
@@ -312,19 +405,193 @@ QCUT_DEV void qcut_red_add(unsigned long long* p, unsigned long long v) {
 }
 
 // Warp-level flush of the packed per-lane counters: tally[t] += ns - 2 * (#odd shots).
+// Branch free: every packed register is widened to two pairs of 16-bit fields (the warp sum is
+// <= 4096) and summed with two REDUX; lane l keeps the totals of terms l, l + 32, l + 64, ... and
+// the warp finishes with ceil(T / 32) coalesced 64-bit reductions to global memory.
 template <int T>
 QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long long* __restrict__ tally) {
+  uint32_t mine[(T + 31) / 32];
+#pragma unroll
+  for (int c = 0; c < (T + 31) / 32; ++c) mine[c] = 0;
+  const bool odd_field = lane & 1;
+  const uint32_t shift = (lane & 2) ? 16u : 0u;
+  const int owner = lane >> 2;  // this lane owns the fields of registers r with r % 8 == owner
 #pragma unroll
   for (int r = 0; r < (T + 3) / 4; ++r) {
-    // Widen the four 8-bit fields to two pairs of 16-bit fields so the warp sum (<= 4096) fits.
     const uint32_t ev = __reduce_add_sync(0xffffffffu, acc[r] & 0x00FF00FFu);         // terms 4r, 4r+2
     const uint32_t od = __reduce_add_sync(0xffffffffu, (acc[r] >> 8) & 0x00FF00FFu);  // terms 4r+1, 4r+3
-    const int t = 4 * r + lane;
-    if (lane < 4 && t < T) {
-      const uint32_t pair = (lane & 1) ? od : ev;
-      const long long odd = (lane & 2) ? (pair >> 16) : (pair & 0xFFFFu);
-      qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2 * odd));
+    const uint32_t val = ((odd_field ? od : ev) >> shift) & 0xFFFFu;
+    if ((r & 7) == owner) mine[r >> 3] = val;
+  }
+#pragma unroll
+  for (int c = 0; c < (T + 31) / 32; ++c) {
+    const int t = 32 * c + lane;
+    if (t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
+  }
+}
+// ---- bulk-copy staged stream of steps (device only) ---------------------------------------------
+// One staging buffer and one mbarrier per warp.  While the warp does the arithmetic of step s, the
+// copy engine brings step s+1 (possibly the first step of the warp's next tile) into the buffer:
+//   wait(full) -> LDS everything into registers -> __syncwarp -> lane 0 issues the next bulk copies
+//   -> transpose + XOR networks of the current step.
+QCUT_DEV uint32_t qcut_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+QCUT_DEV void qcut_mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+QCUT_DEV void qcut_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+QCUT_DEV void qcut_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+QCUT_DEV void qcut_mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "QCUT_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra QCUT_DONE;\n"
+      "bra QCUT_WAIT;\n"
+      "QCUT_DONE:\n"
+      "}" :: "r"(mbar), "r"(parity) : "memory");
+}
+
+template <int NB>
+struct QcutStage {
+  static const int OBS_BYTES = QcutGeo<NB>::STEP_SHOTS * NB;
+  static const int QPD_BYTES = QcutGeo<NB>::STEP_SHOTS;      // staged only when nb_qpd == 1
+  static const int BYTES = OBS_BYTES + QPD_BYTES;            // 9216 / 5120 / 6144 / 8192 for NB = 8 / 4 / 2 / 1
+};
+
+// Issue the bulk copies of one step (lane 0 only).  Sizes are rounded up to 16 bytes: every matrix is
+// readable up to its 16-byte padded end (include/qcut_b200.h).
+template <int NB>
+QCUT_DEV void qcut_stage_issue(uint32_t buf, uint32_t mbar, const uint8_t* obs_s, const uint8_t* qpd_s, int nbq, int n) {
+  const uint32_t ob = ((uint32_t)n * NB + 15u) & ~15u;
+  const uint32_t qb = (nbq == 1) ? (((uint32_t)n + 15u) & ~15u) : 0u;
+  qcut_mbar_expect_tx(mbar, ob + qb);
+  qcut_bulk_g2s(buf, obs_s, ob, mbar);
+  if (qb) qcut_bulk_g2s(buf + QcutStage<NB>::OBS_BYTES, qpd_s, qb, mbar);
+}
+
+template <int NB, class Terms>
+QCUT_DEV void qcut_warp_stream(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,
+                               const QcutTile* __restrict__ tiles, const int64_t n_tiles, int64_t first_tile,
+                               int64_t tile_stride, unsigned long long* __restrict__ tallies, uint8_t* stage,
+                               unsigned long long* mbar_ptr, int lane) {
+  typedef QcutGeo<NB> G;
+  if (first_tile >= n_tiles) return;
+  const uint32_t buf = qcut_smem_addr(stage);
+  const uint32_t mbar = qcut_smem_addr(mbar_ptr);
+  if (lane == 0) qcut_mbar_init(mbar, 1);
+  __syncwarp();
+
+  // current tile
+  int64_t tile = first_tile;
+  QcutTile te = tiles[tile];
+  QcutPub pub = pubs[te.pub];
+  // next tile's descriptors are fetched one tile ahead so their latency never shows
+  QcutTile te_next = te;
+  QcutPub pub_next = pub;
+  bool have_next = tile + tile_stride < n_tiles;
+  if (have_next) { te_next = tiles[tile + tile_stride]; pub_next = pubs[te_next.pub]; }
+
+  int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;
+  int ns = (int)(((int64_t)pub.shots - shot0 < QCUT_TILE_SHOTS) ? (int64_t)pub.shots - shot0 : QCUT_TILE_SHOTS);
+  int nbq = (int)pub.nb_qpd;
+  const uint8_t* obs = data + pub.obs_offset + (uint64_t)shot0 * NB;
+  const uint8_t* qpd = data + pub.qpd_offset + (uint64_t)shot0 * nbq;
+  int s0 = 0;
+  uint32_t parity = 0;
+  if (lane == 0) qcut_stage_issue<NB>(buf, mbar, obs, qpd, nbq, ns < G::STEP_SHOTS ? ns : G::STEP_SHOTS);
+
+  uint32_t acc[Terms::NACC];
+#pragma unroll
+  for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+
+  for (;;) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    const uint8_t* qpd_g = qpd + (uint64_t)s0 * nbq;
+    const bool last_step = s0 + G::STEP_SHOTS >= ns;
+
+    // what comes after this step: the next step of this tile, or the first step of the next tile
+    const uint8_t* n_obs = obs + (uint64_t)(s0 + G::STEP_SHOTS) * NB;
+    const uint8_t* n_qpd = qpd + (uint64_t)(s0 + G::STEP_SHOTS) * nbq;
+    int n_cnt = ns - s0 - G::STEP_SHOTS;
+    int n_nbq = nbq;
+    int64_t n_shot0 = 0;
+    int n_ns = 0;
+    if (last_step && have_next) {
+      n_shot0 = (int64_t)te_next.tile_in_pub * QCUT_TILE_SHOTS;
+      const int64_t left = (int64_t)pub_next.shots - n_shot0;
+      n_ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;
+      n_nbq = (int)pub_next.nb_qpd;
+      n_obs = data + pub_next.obs_offset + (uint64_t)n_shot0 * NB;
+      n_qpd = data + pub_next.qpd_offset + (uint64_t)n_shot0 * n_nbq;
+      n_cnt = n_ns;
     }
+    if (n_cnt > G::STEP_SHOTS) n_cnt = G::STEP_SHOTS;
+    const bool more = !last_step || have_next;
+
+    // ---- consume the staged step ----
+    qcut_mbar_wait(mbar, parity);
+    parity ^= 1u;
+    uint32_t a[G::BLOCKS][32];
+    uint32_t qp[G::BATCHES];
+    const QcutSrcShared src = {buf, buf + (uint32_t)QcutStage<NB>::OBS_BYTES};
+    // (loads only; the arithmetic of qcut_step runs after the next copy has been issued because the
+    //  compiler keeps the shared loads at the top and the volatile copy issue right behind them)
+    if (n == G::STEP_SHOTS) qcut_step_loads<NB, true>(src, n, lane, a);
+    else qcut_step_loads<NB, false>(src, n, lane, a);
+    uint32_t qraw[G::QRAW];
+    const bool q_staged = nbq == 1;
+    if (q_staged) {
+      if (n == G::STEP_SHOTS) qcut_qpd_loads<NB, true>(src, n, lane, qraw);
+      else qcut_qpd_loads<NB, false>(src, n, lane, qraw);
+    }
+    __syncwarp();
+    if (more && lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      qcut_stage_issue<NB>(buf, mbar, n_obs, n_qpd, n_nbq, n_cnt);
+    }
+
+    // ---- arithmetic of the current step ----
+    if (q_staged) qcut_qpd_planes<NB>(qraw, qp);
+    else {
+#pragma unroll
+      for (int u = 0; u < G::BATCHES; ++u) qp[u] = 0;
+      qcut_qp_slow<NB>(qpd_g, nbq, n, lane, qp);
+    }
+#pragma unroll
+    for (int blk = 0; blk < G::BLOCKS; ++blk) qcut_transpose32(a[blk]);
+    if (n != G::STEP_SHOTS) qcut_mask_tail<NB>(n, lane, a, qp);
+#pragma unroll
+    for (int u = 0; u < G::BATCHES; ++u)
+      Terms::run(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], acc);
+
+    if (!last_step) {
+      s0 += G::STEP_SHOTS;
+      continue;
+    }
+    // ---- end of tile: flush, advance ----
+    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);
+#pragma unroll
+    for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+    if (!have_next) break;
+    tile += tile_stride;
+    te = te_next;
+    pub = pub_next;
+    shot0 = n_shot0;
+    ns = n_ns;
+    nbq = n_nbq;
+    obs = n_obs;
+    qpd = n_qpd;
+    s0 = 0;
+    have_next = tile + tile_stride < n_tiles;
+    if (have_next) { te_next = tiles[tile + tile_stride]; pub_next = pubs[te_next.pub]; }
   }
 }
 #endif

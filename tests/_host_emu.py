@@ -30,6 +30,7 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 """
 
 

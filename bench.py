@@ -235,6 +235,7 @@ def ours_arm(args):
     clocks = sampler.stop(t0, t1) if sampler else None
     elapsed = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
     k1 = torch.tensor([np.mean([e[0].elapsed_time(e[1]) for e in ev])], dtype=torch.float64, device="cuda")
+    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     if world > 1:
         dist.barrier()
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
@@ -254,7 +255,7 @@ def ours_arm(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "K1 parity tally (all launches of qcut_tally_launch)",
                 "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms, "peak_source": peak_src,
-                "k1_share_of_step": k1_ms / ms_per_step}
+                "k1_share_of_step": k1_ms / ms_per_step, "k2_plus_allreduce_ms": k2_ms}
 
     # ---- end to end through the public API with host buffers -------------------------------------------
     e2e = None

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define QCUT_ABI_VERSION 2
+#define QCUT_ABI_VERSION 3
 /* Shots per scheduling tile (one warp processes one tile of one PUB at a time). */
 #define QCUT_TILE_SHOTS 4096
 /* Widest observable row (bytes) the kernels accept: 64 bytes = 512 measured qubits per group. */
@@ -132,14 +132,17 @@ int qcut_tally_launch(const qcut_plan* plan, const qcut_schedule* schedule, cons
  * (reference cutting_reconstruction.py:134-136,163-168):
  *   out[k] = sum_i coeff[i] * prod_label mean_{(g,t) in lookup(label,k)} tally / shots
  * with the expectation of PUB (label, i, g) taken as tally/shots (one correctly rounded fp64
- * division).  Deterministic: fixed partition of i, fixed-order combination.  d_workspace must
- * hold qcut_reduce_workspace_bytes(n_coeffs, n_obs) bytes. */
+ * division).  Deterministic: fixed partition of i, fixed-order combination; for n_coeffs <= 1024 the
+ * summation order is exactly the reference's.  d_workspace must hold
+ * qcut_reduce_workspace_bytes(n_coeffs, n_obs) bytes.  single_slot != 0 asserts that every
+ * observable has exactly one lookup slot in every subsystem (what Qiskit's grouping yields): the
+ * kernels then run straight-line code specialised for 1..4 subsystems; 0 selects the general form. */
 size_t qcut_reduce_workspace_bytes(int64_t n_coeffs, int n_obs);
 int qcut_reduce_launch(const int64_t* d_tallies, const qcut_pub_desc* d_pubs,
                        const qcut_label_desc* d_labels, int n_labels,
                        const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                        const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                       void* d_workspace, void* stream);
+                       void* d_workspace, int single_slot, void* stream);
 
 /* ---- SamplerV1 quasi-distributions (reference cutting_reconstruction.py:143-149,173-193) -------
  * For PUB p, outcomes [d_dist_start[p], d_dist_start[p+1]) hold (obs bits, qpd bits, weight):
@@ -157,7 +160,7 @@ int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_p
                                const qcut_label_desc* d_labels, int n_labels,
                                const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                                const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                               void* d_workspace, void* stream);
+                               void* d_workspace, int single_slot, void* stream);
 
 /* ---- host staging: gather many borrowed BitArray buffers into one pinned buffer ---------------
  * Copies n_arrays host buffers (h_src[i], h_bytes[i] bytes) to h_dst + h_dst_offset[i] with

@@ -19,7 +19,7 @@ LIB_PATH = PACKAGE_DIR / "libqcut_b200.so"
 
 TILE_SHOTS = 4096
 MAX_OBS_BYTES = 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 PLAN_NO_JIT = 1
 PLAN_GENERIC_ONLY = 2
 PLAN_STAGED = 4
@@ -91,9 +91,9 @@ SIGNATURES = {
     "qcut_schedule_device_pubs": (_VP, [_VP]),
     "qcut_tally_launch": (_INT, [_VP, _VP, _VP, _VP, _I64, _VP, C.POINTER(_INT)]),
     "qcut_reduce_workspace_bytes": (_SZ, [_I64, _INT]),
-    "qcut_reduce_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _VP]),
+    "qcut_reduce_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
     "qcut_quasi_launch": (_INT, [_VP, _I64, _VP, _VP, _VP, _VP, _INT, _VP, _INT, _VP, _VP, _VP]),
-    "qcut_reduce_expvals_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _VP]),
+    "qcut_reduce_expvals_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
     "qcut_gather_host": (_INT, [_VP, _VP, _VP, _I64, _VP, _INT]),
     "qcut_generate_source": (_SZ, [_VP, _INT, _VP, _SZ, _INT, C.c_char_p, _SZ]),
     "qcut_compile_source": (_INT, [C.c_char_p, C.POINTER(_SZ), _VP, _SZ]),

@@ -45,7 +45,7 @@ int jit_build(qcut_plan* plan);
 void jit_release(qcut_plan* plan);
 template <typename TallyT>
 int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, int, const uint32_t*,
-                  const qcut_slot*, const double*, int64_t, int, double*, void*, cudaStream_t);
+                  const qcut_slot*, const double*, int64_t, int, double*, void*, bool, cudaStream_t);
 size_t reduce_workspace_bytes(int64_t, int);
 int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const uint64_t*, const int64_t*,
                  const uint64_t*, int, const uint64_t*, int, const double*, double*, cudaStream_t);
@@ -289,21 +289,21 @@ size_t qcut_reduce_workspace_bytes(int64_t n_coeffs, int n_obs) { return reduce_
 int qcut_reduce_launch(const int64_t* d_tallies, const qcut_pub_desc* d_pubs, const qcut_label_desc* d_labels,
                        int n_labels, const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                        const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                       void* d_workspace, void* stream) {
+                       void* d_workspace, int single_slot, void* stream) {
   if (!d_out || !d_workspace || n_labels < 0 || n_coeffs < 0)
     return set_error("qcut_reduce_launch: bad argument"), QCUT_ERR_INVALID;
   return launch_reduce<int64_t>(d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs,
-                                n_coeffs, n_obs, d_out, d_workspace, static_cast<cudaStream_t>(stream));
+                                n_coeffs, n_obs, d_out, d_workspace, single_slot != 0, static_cast<cudaStream_t>(stream));
 }
 
 int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_pubs,
                                const qcut_label_desc* d_labels, int n_labels, const uint32_t* d_lookup_start,
                                const qcut_slot* d_lookup, const double* d_coeffs, int64_t n_coeffs, int n_obs,
-                               double* d_out, void* d_workspace, void* stream) {
+                               double* d_out, void* d_workspace, int single_slot, void* stream) {
   if (!d_out || !d_workspace || n_labels < 0 || n_coeffs < 0)
     return set_error("qcut_reduce_expvals_launch: bad argument"), QCUT_ERR_INVALID;
   return launch_reduce<double>(d_expvals, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs,
-                               n_coeffs, n_obs, d_out, d_workspace, static_cast<cudaStream_t>(stream));
+                               n_coeffs, n_obs, d_out, d_workspace, single_slot != 0, static_cast<cudaStream_t>(stream));
 }
 
 int qcut_quasi_launch(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_group_desc* d_groups,

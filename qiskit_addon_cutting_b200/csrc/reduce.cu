@@ -12,7 +12,8 @@
 //            -> shared memory;
 //   phase 2 (one thread per observable): sums its row in strictly ascending i, separate multiply and
 //            add, no FMA contraction -- the reference's order and rounding.
-// Chunks are combined in ascending order by a second launch.  For n_coeffs <= kReduceChunk the
+// Chunks (1024 tuples when the whole problem fits one chunk, else 256) are combined in ascending
+// order by a second launch.  For n_coeffs <= kReduceChunk the
 // summation order is therefore *identical* to the reference's; in every case it is deterministic.
 #include <type_traits>
 
@@ -23,72 +24,232 @@ namespace qcut {
 constexpr int kReduceChunk = 1024;
 constexpr int kReduceObs = 8;
 constexpr int kReduceThreads = 256;
-constexpr int kReduceRow = kReduceChunk + 2;  // padded row (doubles) so the 8 rows start in different banks
 
 template <typename TallyT>
 __device__ __forceinline__ double pub_expval(const TallyT* __restrict__ tallies,
                                              const qcut_pub_desc* __restrict__ pub, uint32_t term);
+
+// The two halves of a PUB descriptor that K2 needs, fetched with two independent 8-byte loads
+// (no branch between them: the dependent tally load can be issued as soon as the offset arrives).
+struct PubRef {
+  uint64_t tally_offset;
+  uint32_t shots;
+};
+__device__ __forceinline__ PubRef load_pub_ref(const qcut_pub_desc* __restrict__ pub) {
+  const unsigned long long off = __ldg(reinterpret_cast<const unsigned long long*>(&pub->tally_offset));
+  const uint2 sg = __ldg(reinterpret_cast<const uint2*>(&pub->shots));  // {shots, group}
+  return PubRef{off, sg.x};
+}
 
 // V2: exact int64 tally -> one correctly rounded division.  A PUB with zero shots contributes
 // 0.0, as the reference's empty shot loop does (cutting_reconstruction.py:155-161).
 template <>
 __device__ __forceinline__ double pub_expval<int64_t>(const int64_t* __restrict__ tallies,
                                                       const qcut_pub_desc* __restrict__ pub, uint32_t term) {
-  const uint32_t shots = __ldg(&pub->shots);
-  if (shots == 0) return 0.0;
-  return __ddiv_rn((double)__ldg(tallies + __ldg(&pub->tally_offset) + term), (double)shots);
+  const PubRef ref = load_pub_ref(pub);
+  const double tally = (double)__ldg(tallies + ref.tally_offset + term);
+  const double e = __ddiv_rn(tally, (double)(ref.shots ? ref.shots : 1u));
+  return ref.shots ? e : 0.0;
 }
 
 // V1: the quasi-probability kernel already produced fp64 expectation values.
 template <>
 __device__ __forceinline__ double pub_expval<double>(const double* __restrict__ expvals,
                                                      const qcut_pub_desc* __restrict__ pub, uint32_t term) {
-  return __ldg(expvals + __ldg(&pub->tally_offset) + term);
+  return __ldg(expvals + __ldg(reinterpret_cast<const unsigned long long*>(&pub->tally_offset)) + term);
 }
 
 template <typename TallyT>
+__device__ __forceinline__ double expval_from(TallyT raw, uint32_t shots);
+template <>
+__device__ __forceinline__ double expval_from<int64_t>(int64_t raw, uint32_t shots) {
+  const double e = __ddiv_rn((double)raw, (double)(shots ? shots : 1u));
+  return shots ? e : 0.0;
+}
+template <>
+__device__ __forceinline__ double expval_from<double>(double raw, uint32_t) { return raw; }
+
+// One hoisted (subsystem, observable) slot: where to find E[label, i, .] for this thread's observable.
+struct SlotRef {
+  uint64_t pub_base;
+  uint32_t n_groups, group, term;
+};
+
+// term[j] = coeff[i_j] * prod_l E[l, i_j] for B tuples at once.  Straight-line code (L and B are
+// compile-time): all B x L descriptor loads are issued first, then all B x L tally loads, then the
+// arithmetic -- the two-level load chains overlap instead of running one after the other.
+template <typename TallyT, int L, int B>
+__device__ __forceinline__ void batch_terms(const TallyT* __restrict__ tallies, const qcut_pub_desc* __restrict__ pubs,
+                                            const SlotRef* slots, const double* __restrict__ coeffs,
+                                            const int64_t* idx, double* term) {
+  PubRef ref[B][L];
+#pragma unroll
+  for (int j = 0; j < B; ++j)
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+      ref[j][l] = load_pub_ref(pubs + slots[l].pub_base + (uint64_t)idx[j] * slots[l].n_groups + slots[l].group);
+  TallyT raw[B][L];
+  double c[B];
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    c[j] = __ldg(coeffs + idx[j]);
+#pragma unroll
+    for (int l = 0; l < L; ++l) raw[j][l] = __ldg(tallies + ref[j][l].tally_offset + slots[l].term);
+  }
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    double prod = 1.0;
+#pragma unroll
+    for (int l = 0; l < L; ++l) prod = __dmul_rn(prod, expval_from<TallyT>(raw[j][l], ref[j][l].shots));  // mean of one slot = itself
+    term[j] = __dmul_rn(c[j], prod);
+  }
+}
+
+// Hoist the slots of observable k; false if some subsystem lists more than one slot for it.
+template <int L>
+__device__ __forceinline__ bool load_slots(const qcut_label_desc* __restrict__ labels,
+                                           const uint32_t* __restrict__ lookup_start,
+                                           const qcut_slot* __restrict__ lookup, int k, SlotRef* slots) {
+  bool ok = true;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const qcut_label_desc lab = labels[l];
+    const uint32_t e0 = __ldg(lookup_start + lab.lookup_base + k);
+    const uint32_t e1 = __ldg(lookup_start + lab.lookup_base + k + 1);
+    const qcut_slot slot = lookup[e0];
+    slots[l] = SlotRef{lab.pub_base, lab.num_groups, slot.group, slot.term};
+    ok = ok && (e1 - e0 == 1);
+  }
+  return ok;
+}
+
+// General (slow) form: any number of subsystems, any number of slots per observable.
+template <typename TallyT>
+__device__ __forceinline__ double general_term(const TallyT* __restrict__ tallies, const qcut_pub_desc* __restrict__ pubs,
+                                               const qcut_label_desc* __restrict__ labels, int n_labels,
+                                               const uint32_t* __restrict__ lookup_start,
+                                               const qcut_slot* __restrict__ lookup, const double* __restrict__ coeffs,
+                                               int64_t i, int k) {
+  double prod = 1.0;
+  for (int l = 0; l < n_labels; ++l) {
+    const qcut_label_desc lab = labels[l];
+    const uint32_t e0 = __ldg(lookup_start + lab.lookup_base + k);
+    const uint32_t e1 = __ldg(lookup_start + lab.lookup_base + k + 1);
+    double acc = 0.0;
+    for (uint32_t e = e0; e < e1; ++e) {
+      const qcut_slot slot = lookup[e];
+      acc = __dadd_rn(acc, pub_expval<TallyT>(tallies, pubs + lab.pub_base + (uint64_t)i * lab.num_groups + slot.group, slot.term));
+    }
+    prod = __dmul_rn(prod, __ddiv_rn(acc, (double)(e1 - e0)));  // np.mean of the slot list: sum / n
+  }
+  return __dmul_rn(__ldg(coeffs + i), prod);
+}
+
+constexpr int kMaxFastLabels = 4;  // subsystems handled by the straight-line path (more: general path)
+
+// CHUNK coefficient tuples per CTA (one-chunk problems: reference order end to end).
+// L = number of subsystems when every observable has exactly one slot per subsystem (1..4), 0 = general.
+template <typename TallyT, int CHUNK, int L>
 __global__ void __launch_bounds__(kReduceThreads)
 reduce_partial_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* __restrict__ pubs,
                       const qcut_label_desc* __restrict__ labels, int n_labels,
                       const uint32_t* __restrict__ lookup_start, const qcut_slot* __restrict__ lookup,
                       const double* __restrict__ coeffs, int64_t n_coeffs, int n_obs,
                       double* __restrict__ partial) {
-  extern __shared__ double s_term[];  // [kReduceObs][kReduceRow]
+  constexpr int ROW = CHUNK + 10;  // padded row (doubles): rows start in different banks, room for the 8-wide tail
+  constexpr int B = (L <= 2) ? 8 : 4;
+  constexpr int kStride = kReduceThreads / kReduceObs;  // 32 tuples per pass
+  extern __shared__ double s_term[];  // [kReduceObs][ROW]
   const int k_local = threadIdx.x % kReduceObs;
   const int i_local = threadIdx.x / kReduceObs;
   const int k = blockIdx.x * kReduceObs + k_local;
-  const int64_t i0 = (int64_t)blockIdx.y * kReduceChunk;
-  const int n_i = (int)min((int64_t)kReduceChunk, n_coeffs - i0);
+  const int64_t i0 = (int64_t)blockIdx.y * CHUNK;
+  const int n_i = (int)min((int64_t)CHUNK, n_coeffs - i0);
 
   if (k < n_obs) {
-    for (int ii = i_local; ii < n_i; ii += kReduceThreads / kReduceObs) {
-      const int64_t i = i0 + ii;
-      double prod = 1.0;
-      for (int l = 0; l < n_labels; ++l) {
-        const qcut_label_desc lab = labels[l];
-        const uint32_t e0 = __ldg(lookup_start + lab.lookup_base + k);
-        const uint32_t e1 = __ldg(lookup_start + lab.lookup_base + k + 1);
-        double acc = 0.0;
-        for (uint32_t e = e0; e < e1; ++e) {
-          const qcut_slot slot = lookup[e];
-          acc = __dadd_rn(acc, pub_expval<TallyT>(tallies, pubs + lab.pub_base + (uint64_t)i * lab.num_groups + slot.group, slot.term));
-        }
-        // np.mean of the slot list: sum / n (exactly the value itself for the usual n == 1).
-        prod = __dmul_rn(prod, __ddiv_rn(acc, (double)(e1 - e0)));
+    if constexpr (L > 0) {
+      SlotRef slots[L];
+      load_slots<L>(labels, lookup_start, lookup, k, slots);
+      for (int base = i_local; base < n_i; base += B * kStride) {
+        int64_t idx[B];
+        double term[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) idx[j] = i0 + min(base + j * kStride, n_i - 1);  // clamped: always valid
+        batch_terms<TallyT, L, B>(tallies, pubs, slots, coeffs, idx, term);
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+          if (base + j * kStride < n_i) s_term[k_local * ROW + base + j * kStride] = term[j];
       }
-      s_term[k_local * kReduceRow + ii] = __dmul_rn(__ldg(coeffs + i), prod);
+    } else {
+      for (int ii = i_local; ii < n_i; ii += kStride)
+        s_term[k_local * ROW + ii] = general_term<TallyT>(tallies, pubs, labels, n_labels, lookup_start, lookup, coeffs, i0 + ii, k);
     }
+  }
+  // zero the row tails up to a multiple of 8 so that phase 2 can run 8-wide without bound checks
+  // (adding +0.0 never changes a sum that started at +0.0)
+  const int n_pad = (n_i + 7) & ~7;
+  if (threadIdx.x < kReduceObs * 8) {
+    const int ii = n_i + threadIdx.x / kReduceObs;
+    if (ii < n_pad) s_term[(threadIdx.x % kReduceObs) * ROW + ii] = 0.0;
   }
   __syncthreads();
   if (threadIdx.x < kReduceObs) {
     const int kk = blockIdx.x * kReduceObs + threadIdx.x;
     if (kk < n_obs) {
-      const double* __restrict__ row = s_term + threadIdx.x * kReduceRow;
+      const double* __restrict__ row = s_term + threadIdx.x * ROW;
       double sum = 0.0;
-      for (int ii = 0; ii < n_i; ++ii) sum = __dadd_rn(sum, row[ii]);
+      for (int ii = 0; ii < n_pad; ii += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = row[ii + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum = __dadd_rn(sum, v[j]);  // strictly ascending i
+      }
       partial[(int64_t)blockIdx.y * n_obs + kk] = sum;
     }
   }
+}
+
+// Large problems (more than kReduceChunk tuples): lane <-> observable, one warp walks kStreamChunk
+// consecutive tuples and every lane keeps its running sum in a register (ascending i inside the
+// chunk).  No shared memory; the descriptor -> tally load chains of B tuples x L subsystems are in
+// flight together per lane and up to 64 warps per SM hide the rest of the latency.
+constexpr int kStreamChunk = 256;
+constexpr int kStreamWarps = 4;
+
+template <typename TallyT, int L>
+__global__ void __launch_bounds__(kStreamWarps * 32)
+reduce_stream_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* __restrict__ pubs,
+                     const qcut_label_desc* __restrict__ labels, int n_labels,
+                     const uint32_t* __restrict__ lookup_start, const qcut_slot* __restrict__ lookup,
+                     const double* __restrict__ coeffs, int64_t n_coeffs, int n_obs, int64_t n_chunks,
+                     double* __restrict__ partial) {
+  constexpr int B = (L <= 2) ? 8 : 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t)blockIdx.y * kStreamWarps + (threadIdx.x >> 5);
+  const int k = blockIdx.x * 32 + lane;
+  if (chunk >= n_chunks || k >= n_obs) return;
+  const int64_t i0 = chunk * kStreamChunk;
+  const int n_i = (int)min((int64_t)kStreamChunk, n_coeffs - i0);
+  double sum = 0.0;
+  if constexpr (L > 0) {
+    SlotRef slots[L];
+    load_slots<L>(labels, lookup_start, lookup, k, slots);
+    for (int base = 0; base < n_i; base += B) {
+      int64_t idx[B];
+      double term[B];
+#pragma unroll
+      for (int j = 0; j < B; ++j) idx[j] = i0 + min(base + j, n_i - 1);  // clamped: always a valid tuple
+      batch_terms<TallyT, L, B>(tallies, pubs, slots, coeffs, idx, term);
+#pragma unroll
+      for (int j = 0; j < B; ++j)
+        if (base + j < n_i) sum = __dadd_rn(sum, term[j]);  // ascending i
+    }
+  } else {
+    for (int ii = 0; ii < n_i; ++ii)
+      sum = __dadd_rn(sum, general_term<TallyT>(tallies, pubs, labels, n_labels, lookup_start, lookup, coeffs, i0 + ii, k));
+  }
+  partial[chunk * n_obs + k] = sum;
 }
 
 __global__ void __launch_bounds__(128)
@@ -97,37 +258,80 @@ reduce_combine_kernel(const double* __restrict__ partial, int64_t n_chunks, int 
   const int k = blockIdx.x * 128 + threadIdx.x;
   if (k >= n_obs) return;
   double sum = 0.0;
-  for (int64_t c = 0; c < n_chunks; ++c) sum = __dadd_rn(sum, partial[c * n_obs + k]);
+  for (int64_t c0 = 0; c0 < n_chunks; c0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t c = c0 + j;
+      v[j] = __ldg(partial + (c < n_chunks ? c : n_chunks - 1) * n_obs + k);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < n_chunks) sum = __dadd_rn(sum, v[j]);  // ascending chunk order
+  }
   out[k] = sum;
 }
 
+static int chunk_size(int64_t n_coeffs) { return n_coeffs <= kReduceChunk ? kReduceChunk : kStreamChunk; }
+
 static int64_t num_chunks(int64_t n_coeffs) {
-  return n_coeffs <= 0 ? 1 : (n_coeffs + kReduceChunk - 1) / kReduceChunk;
+  const int chunk = chunk_size(n_coeffs);
+  return n_coeffs <= 0 ? 1 : (n_coeffs + chunk - 1) / chunk;
 }
 
+template <typename TallyT, int L>
+static int launch_level(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qcut_label_desc* d_labels,
+                        int n_labels, const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
+                        const double* d_coeffs, int64_t n_coeffs, int n_obs, double* partial, int64_t chunks,
+                        cudaStream_t stream) {
+  if (chunk_size(n_coeffs) == kReduceChunk) {
+    static bool configured = false;
+    const size_t smem = sizeof(double) * kReduceObs * (kReduceChunk + 10);
+    if (!configured) {
+      QCUT_CUDA(cudaFuncSetAttribute(reduce_partial_kernel<TallyT, kReduceChunk, L>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    const dim3 grid((n_obs + kReduceObs - 1) / kReduceObs, (unsigned)chunks);
+    reduce_partial_kernel<TallyT, kReduceChunk, L><<<grid, kReduceThreads, smem, stream>>>(
+        d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, partial);
+  } else {
+    const dim3 grid((n_obs + 31) / 32, (unsigned)((chunks + kStreamWarps - 1) / kStreamWarps));
+    reduce_stream_kernel<TallyT, L><<<grid, kStreamWarps * 32, 0, stream>>>(
+        d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, chunks, partial);
+  }
+  QCUT_CUDA(cudaGetLastError());
+  return QCUT_OK;
+}
+
+// single_slot: host-side knowledge that every observable has exactly one (group, term) slot in every
+// subsystem (what Qiskit's grouping produces; checked by the caller from the lookup table it uploads).
 template <typename TallyT>
 int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qcut_label_desc* d_labels,
                   int n_labels, const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                   const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                  void* d_workspace, cudaStream_t stream) {
+                  void* d_workspace, bool single_slot, cudaStream_t stream) {
   if (n_obs <= 0) return QCUT_OK;
   const int64_t chunks = num_chunks(n_coeffs);
-  if (chunks > 65535) {
-    set_error("qcut_reduce_launch: more than 65535 * 1024 coefficients per rank are not supported");
+  if (chunks > 65535 * (int64_t)kStreamWarps) {
+    set_error("qcut_reduce_launch: too many coefficients per rank");
     return QCUT_ERR_INVALID;
   }
-  static bool configured[2] = {false, false};
-  const size_t smem = sizeof(double) * kReduceObs * kReduceRow;  // 64 KB + padding
-  const int which = sizeof(TallyT) == sizeof(int64_t) && std::is_same<TallyT, int64_t>::value ? 0 : 1;
-  if (!configured[which]) {
-    QCUT_CUDA(cudaFuncSetAttribute(reduce_partial_kernel<TallyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[which] = true;
-  }
   double* partial = static_cast<double*>(d_workspace);
-  const dim3 grid((n_obs + kReduceObs - 1) / kReduceObs, (unsigned)chunks);
-  reduce_partial_kernel<TallyT><<<grid, kReduceThreads, smem, stream>>>(
-      d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, partial);
-  QCUT_CUDA(cudaGetLastError());
+  const int level = (single_slot && n_labels >= 1 && n_labels <= kMaxFastLabels) ? n_labels : 0;
+  int rc;
+#define QCUT_LEVEL(LV)                                                                                              \
+  rc = launch_level<TallyT, LV>(d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, \
+                                n_obs, partial, chunks, stream)
+  switch (level) {
+    case 1: QCUT_LEVEL(1); break;
+    case 2: QCUT_LEVEL(2); break;
+    case 3: QCUT_LEVEL(3); break;
+    case 4: QCUT_LEVEL(4); break;
+    default: QCUT_LEVEL(0); break;
+  }
+#undef QCUT_LEVEL
+  if (rc != QCUT_OK) return rc;
   reduce_combine_kernel<<<(n_obs + 127) / 128, 128, 0, stream>>>(partial, chunks, n_obs, d_out);
   QCUT_CUDA(cudaGetLastError());
   return QCUT_OK;
@@ -135,10 +339,10 @@ int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qc
 
 template int launch_reduce<int64_t>(const int64_t*, const qcut_pub_desc*, const qcut_label_desc*, int,
                                     const uint32_t*, const qcut_slot*, const double*, int64_t, int,
-                                    double*, void*, cudaStream_t);
+                                    double*, void*, bool, cudaStream_t);
 template int launch_reduce<double>(const double*, const qcut_pub_desc*, const qcut_label_desc*, int,
                                    const uint32_t*, const qcut_slot*, const double*, int64_t, int,
-                                   double*, void*, cudaStream_t);
+                                   double*, void*, bool, cudaStream_t);
 
 size_t reduce_workspace_bytes(int64_t n_coeffs, int n_obs) {
   return (size_t)num_chunks(n_coeffs) * (size_t)(n_obs > 0 ? n_obs : 1) * sizeof(double);

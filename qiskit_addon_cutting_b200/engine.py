@@ -129,6 +129,11 @@ class HostTables:
         return int(((self.pubs["shots"].astype(np.int64) + TILE_SHOTS - 1) // TILE_SHOTS).sum())
 
     @property
+    def single_slot(self) -> bool:
+        """Every observable has exactly one (group, term) slot in every subsystem (the usual case)."""
+        return bool(np.all(np.diff(self.lookup_start.astype(np.int64)) == 1))
+
+    @property
     def work(self) -> int:
         """shots x terms of this table (the unit of BASELINE.json's metric)."""
         return int((self.pubs["shots"].astype(np.int64) * self.groups["n_terms"][self.pubs["group"]]).sum())
@@ -276,6 +281,7 @@ class DeviceBatch:
                 t.n_obs,
                 self.out.data_ptr(),
                 self.workspace.data_ptr(),
+                int(t.single_slot),
                 _stream_ptr(),
             ),
             "qcut_reduce_launch",

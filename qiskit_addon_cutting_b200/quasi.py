@@ -105,7 +105,8 @@ def reconstruct_v1(results: list, collections: list, coeffs: np.ndarray, i_lo: i
     check(
         lib.qcut_reduce_expvals_launch(
             expvals.data_ptr(), d_pubs.data_ptr(), d_labels.data_ptr(), len(label_rows), d_ls.data_ptr(),
-            d_lk.data_ptr(), d_coeffs.data_ptr(), i_hi - i_lo, n_obs, out.data_ptr(), ws.data_ptr(), stream,
+            d_lk.data_ptr(), d_coeffs.data_ptr(), i_hi - i_lo, n_obs, out.data_ptr(), ws.data_ptr(),
+            int(np.all(np.diff(np.array(lookup_start, dtype=np.int64)) == 1)), stream,
         ),
         "qcut_reduce_expvals_launch",
     )

@@ -151,3 +151,18 @@ def test_large_chunked_reduction_matches_oracle(lib):
     out = np.array(reconstruct_expectation_values(results, coefficients, observables))
     want = np.array(oracle.reconstruct_exact(results, coefficients, observables))
     assert np.max(np.abs(out - want)) <= 1e-12
+
+
+@pytest.mark.parametrize("n_labels,C", [(1, 3), (3, 40), (5, 7), (6, 1500)])
+def test_reduction_for_any_number_of_subsystems(lib, n_labels, C):
+    """K2 runs straight-line code for 1..4 subsystems and the general form beyond; both chunkings (C <= / > 1024)."""
+    rng = np.random.default_rng(100 * n_labels + C)
+    observables = {f"L{j}": _cases.random_paulis(rng, 6, 5 + j, 0, 4) for j in range(n_labels)}
+    coefficients = _cases.random_coefficients(rng, C, kappa=27.0)
+    results = _cases.make_results(observables, C, 48, 2, seed=int(rng.integers(1 << 30)))
+    out = np.array(reconstruct_expectation_values(results, coefficients, observables))
+    want = np.array(oracle.reconstruct_exact(results, coefficients, observables))
+    if C <= 1024:
+        assert _hex(out) == _hex(want)
+    else:
+        assert np.max(np.abs(out - want)) <= 1e-13 * 27.0

@@ -25,24 +25,24 @@ constexpr uint32_t kMaxJitTerms = 384;  // packed 8-bit counters: ceil(T/4) regi
 
 bool jit_supports(const qcut_group_desc& gd) {
   const uint32_t nb = gd.nb_obs;
-  return (nb == 1 || nb == 2 || nb == 4 || nb == 8) && gd.n_terms > 0 && gd.n_terms <= kMaxJitTerms;
+  return nb >= 1 && nb <= 8 && gd.n_terms > 0 && gd.n_terms <= kMaxJitTerms;
 }
 
 // Name of the register holding plane (byte B, bit b) for NB-byte rows (see sliced_prelude.cuh).
 static std::string plane_name(uint32_t nb, uint32_t byte, uint32_t bit) {
   std::ostringstream os;
-  if (nb == 8 && byte >= 4) os << "Q[" << 8 * (byte - 4) + bit << "]";
+  if (byte >= 4) os << "Q[" << 8 * (byte - 4) + bit << "]";
   else os << "P[" << 8 * (byte % 4) + bit << "]";
   return os.str();
 }
 
 // The translation unit for one group.  Pure host code.
 std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out,
-                                   bool staged, int threads) {
+                                   bool staged, int threads, int prefetch) {
   if (!jit_supports(gd)) return std::string();
   const uint32_t T = gd.n_terms, nb = gd.nb_obs;
   // Register budget: 32 per block + packed counters + ~28 of addressing / temporaries.
-  int min_blocks = ((nb == 8 ? 64 : 32) + (int)((T + 3) / 4) + 28 > 128) ? 1 : 2;
+  int min_blocks = ((nb > 4 ? 64 : 32) + (int)((T + 3) / 4) + 28 > 128) ? 1 : 2;
   if (min_blocks_out && *min_blocks_out > 0) min_blocks = *min_blocks_out;  // explicit override
   if (min_blocks_out) *min_blocks_out = min_blocks;
 
@@ -83,25 +83,67 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
           "                                     (int64_t)gridDim.x * n_warps_cta, tallies, stage, mbar, lane);\n"
           "}\n";
   } else {
+    if (prefetch < 2) {
+      // Direct loads, plain grid-stride loop over the tile list (prefetch == 1: L2-prefetch the next
+      // step of the same tile).
+      os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+            "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+            "                  unsigned long long* __restrict__ tallies) {\n"
+            "  const int lane = threadIdx.x & 31;\n"
+            "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+            "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
+            "       tile += n_warps) {\n"
+            "    const QcutTile te = tiles[tile];\n"
+            "    const QcutPub pub = pubs[te.pub];\n"
+            "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+            "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+            "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+            "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
+            "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+            "    uint32_t acc[Terms::NACC];\n";
+      if (prefetch == 1)
+        os << "    qcut_lane_tile_pf<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc, obs, qpd, 1, 0);\n";
+      else
+        os << "    qcut_lane_tile<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n";
+      os << "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
+            "  }\n"
+            "}\n";
+    } else {
+    // Direct loads; the tile entry and PUB descriptor of the warp's next tile are fetched one tile
+    // ahead, and every step L2-prefetches the bytes of the step that follows it.
     os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
           "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
           "                  unsigned long long* __restrict__ tallies) {\n"
           "  const int lane = threadIdx.x & 31;\n"
           "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
-          "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
-          "       tile += n_warps) {\n"
-          "    const QcutTile te = tiles[tile];\n"
-          "    const QcutPub pub = pubs[te.pub];\n"
+          "  int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);\n"
+          "  if (tile >= n_tiles) return;\n"
+          "  QcutTile te = tiles[tile];\n"
+          "  QcutPub pub = pubs[te.pub];\n"
+          "  for (;;) {\n"
+          "    const int64_t next = tile + n_warps;\n"
+          "    const bool have_next = next < n_tiles;\n"
+          "    QcutTile te_n = te;\n"
+          "    QcutPub pub_n = pub;\n"
+          "    if (have_next) { te_n = tiles[next]; pub_n = pubs[te_n.pub]; }\n"
           "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
           "    const int64_t left = (int64_t)pub.shots - shot0;\n"
           "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
           "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
           "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "    const int64_t shot0_n = (int64_t)te_n.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "    const int64_t left_n = (int64_t)pub_n.shots - shot0_n;\n"
+          "    const int ns_n = !have_next ? 0 : (left_n < QCUT_TILE_SHOTS ? (int)left_n : QCUT_TILE_SHOTS);\n"
           "    uint32_t acc[Terms::NACC];\n"
-          "    qcut_lane_tile<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n"
+          "    qcut_lane_tile_pf<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc,\n"
+          "        data + pub_n.obs_offset + (uint64_t)shot0_n * Terms::NB,\n"
+          "        data + pub_n.qpd_offset + (uint64_t)shot0_n * pub_n.nb_qpd, (int)pub_n.nb_qpd, ns_n);\n"
           "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
+          "    if (!have_next) break;\n"
+          "    tile = next; te = te_n; pub = pub_n;\n"
           "  }\n"
           "}\n";
+    }
   }
   os << "#else  // host emulation entry: one lane of one tile, unpacked odd counts\n";
   os << "extern \"C\" int qcut_emu_lane_tile(const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
@@ -135,7 +177,11 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
         "  switch (nb) {\n"
         "    case 1: return qcut_emu_rt<1>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
         "    case 2: return qcut_emu_rt<2>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
+        "    case 3: return qcut_emu_rt<3>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
         "    case 4: return qcut_emu_rt<4>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
+        "    case 5: return qcut_emu_rt<5>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
+        "    case 6: return qcut_emu_rt<6>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
+        "    case 7: return qcut_emu_rt<7>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
         "    case 8: return qcut_emu_rt<8>(obs, qpd, nbq, ns, lane, mw, n_words, T, odd_out);\n"
         "    default: return -1;\n"
         "  }\n"
@@ -200,7 +246,9 @@ int jit_build(qcut_plan* plan) {
     jk.threads = env_threads ? std::atoi(env_threads) : 256;
     if (jk.threads < 32 || jk.threads > 1024 || jk.threads % 32) jk.threads = 256;
     jk.min_blocks = env_blocks ? std::atoi(env_blocks) : 0;
-    jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads);
+    const char* env_pf = std::getenv("QCUT_JIT_PREFETCH");
+    const int prefetch = env_pf ? std::atoi(env_pf) : 0;
+    jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads, prefetch);
     rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
   };
   std::vector<std::thread> pool;
@@ -218,7 +266,8 @@ int jit_build(qcut_plan* plan) {
     if (err != cudaSuccess) return cuda_fail(err, "cudaLibraryLoadData(qcut_tally_sliced)");
     if (jk.staged) {
       // per warp: one step of observable rows + one step of qpd bytes, plus one mbarrier
-      const int stage = jk.nb_obs == 8 ? 9216 : jk.nb_obs == 4 ? 5120 : jk.nb_obs == 2 ? 6144 : 8192;
+      const int step_shots = jk.nb_obs == 1 ? 4096 : jk.nb_obs == 2 ? 2048 : 1024;
+      const int stage = step_shots * (jk.nb_obs + 1);
       jk.smem_bytes = (jk.threads / 32) * (stage + 8);
       int dev = 0;
       QCUT_CUDA(cudaGetDevice(&dev));
@@ -266,7 +315,7 @@ size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const
   if (!h_groups || group < 0 || group >= n_groups) return 0;
   const qcut_group_desc& gd = h_groups[group];
   if ((size_t)gd.mask_offset + (size_t)gd.n_terms * gd.nb_obs > mask_bytes) return 0;
-  const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, true, 256);
+  const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, false, 256, 0);
   if (src.empty()) return 0;
   if (buf && buf_len) {
     const size_t n = src.size() < buf_len - 1 ? src.size() : buf_len - 1;

@@ -18,6 +18,9 @@
 //   NB = 4:  8 chunks, row 4k+e = shot 4*(32k+lane)+e,                                 1024 shots
 //   NB = 2:  8 chunks, row 4k+e holds shots 8*(32k+lane)+2e+{0,1}  (2 batches),        2048 shots
 //   NB = 1:  8 chunks, row 4k+e holds shots 16*(32k+lane)+4e+{0..3} (4 batches),       4096 shots
+//   NB = 3, 5, 6, 7 ("grouped" layout): a lane owns two groups of 16 consecutive shots (16*NB contiguous
+//           bytes = NB 16-byte loads each, L1-allocating because neighbouring lanes share sectors); the rows
+//           are cut out of the loaded words with one PRMT each; row 16g+r = shot 16*(32g+lane)+r, 1024 shots
 // After the transposition, plane (byte B, bit b) of batch u is register 8*(B%4)+b + PLANES*u of
 // block B/4, i.e. "memory bit" 8*B+b of the row: masks are used in memory order, never byte swapped.
 #pragma once
@@ -63,10 +66,16 @@ QCUT_DEV qcut_u4 qcut_ld16(const uint8_t* p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+QCUT_DEV qcut_u4 qcut_ld16_l1(const uint8_t* p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  qcut_u4 r = {v.x, v.y, v.z, v.w};
+  return r;
+}
 QCUT_DEV uint32_t qcut_ld4(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 QCUT_DEV uint32_t qcut_ld2(const uint8_t* p) { return __ldg(reinterpret_cast<const uint16_t*>(p)); }
 QCUT_DEV uint32_t qcut_ld1(const uint8_t* p) { return __ldg(p); }
 #else
+QCUT_DEV qcut_u4 qcut_ld16_l1(const uint8_t* p) { qcut_u4 v; memcpy(&v, p, 16); return v; }
 QCUT_DEV qcut_u4 qcut_ld16(const uint8_t* p) { qcut_u4 v; memcpy(&v, p, 16); return v; }
 QCUT_DEV uint32_t qcut_ld4(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 QCUT_DEV uint32_t qcut_ld2(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
@@ -83,6 +92,9 @@ struct QcutSrcGlobal {
   const uint8_t* obs;
   const uint8_t* qpd;
   QCUT_MDEV qcut_u4 obs16(int off) const { return qcut_ld16(obs + off); }
+  // grouped layout: neighbouring lanes' 16-byte pieces share 32-byte sectors across consecutive
+  // loads, so these go through L1 (allocate) instead of bypassing it
+  QCUT_MDEV qcut_u4 obs16_shared_sectors(int off) const { return qcut_ld16_l1(obs + off); }
   QCUT_MDEV qcut_u4 qpd16(int off) const { return qcut_ld16(qpd + off); }
   QCUT_MDEV uint32_t qpd4(int off) const { return qcut_ld4(qpd + off); }
   QCUT_MDEV uint32_t qpd2(int off) const { return qcut_ld2(qpd + off); }
@@ -97,6 +109,7 @@ struct QcutSrcShared {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(obs + off));
     return v;
   }
+  QCUT_MDEV qcut_u4 obs16_shared_sectors(int off) const { return obs16(off); }
   QCUT_MDEV qcut_u4 qpd16(int off) const {
     qcut_u4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(qpd + off));
@@ -172,20 +185,22 @@ QCUT_DEV uint32_t qcut_byte_parity(uint32_t v) {
 
 template <int NB>
 struct QcutGeo {
-  static const int CHUNKS = (NB == 8) ? 16 : 8;       // 16-byte loads per lane per step
-  static const int BLOCKS = (NB == 8) ? 2 : 1;        // 32x32 blocks per lane per step
-  static const int BATCHES = (NB >= 4) ? 1 : 4 / NB;  // 32-shot batches per block
-  static const int SPC = 16 / NB;                     // shots per chunk
-  static const int RPC = (NB == 8) ? 2 : 4;           // rows per chunk (per block)
-  static const int STEP_SHOTS = CHUNKS * 32 * SPC;
-  static const int PLANES = 32 / BATCHES;             // registers per batch in one block
-  static const int QRAW = (NB == 1) ? 32 : (NB == 2) ? 16 : 8;  // raw qpd words per lane per step
+  static const bool GROUPED = !(NB == 1 || NB == 2 || NB == 4 || NB == 8);  // row width not a power of two
+  static const int CHUNKS = GROUPED ? 2 * NB : (NB == 8) ? 16 : 8;   // 16-byte loads per lane per step
+  static const int BLOCKS = (NB + 3) / 4;                             // 32x32 blocks per lane per step
+  static const int BATCHES = (NB >= 3) ? 1 : 4 / NB;                  // 32-shot batches per block
+  static const int SPC = GROUPED ? 16 : 16 / NB;                      // shots per chunk (per group when GROUPED)
+  static const int RPC = (NB == 8) ? 2 : 4;                           // rows per chunk (power-of-two layouts)
+  static const int STEP_SHOTS = GROUPED ? 1024 : CHUNKS * 32 * SPC;
+  static const int PLANES = 32 / BATCHES;                             // registers per batch in one block
+  static const int QRAW = (NB == 1) ? 32 : (NB == 2) ? 16 : 8;        // raw qpd words per lane per step
 };
 
 // Shot (relative to the step) held by row j, sub-shot u of this lane.
 template <int NB>
 QCUT_DEV int qcut_shot_of(int j, int u, int lane) {
   typedef QcutGeo<NB> G;
+  if constexpr (G::GROUPED) return ((j >> 4) * 32 + lane) * 16 + (j & 15);
   const int k = j / G::RPC, e = j % G::RPC;
   return (k * 32 + lane) * G::SPC + e * G::BATCHES + u;
 }
@@ -217,15 +232,40 @@ QCUT_DEV void qcut_qp_slow(const uint8_t* __restrict__ qpd_s, int nbq, int n, in
 template <int NB, bool FULL, class Src>
 QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32]) {
   typedef QcutGeo<NB> G;
+  if constexpr (G::GROUPED) {
 #pragma unroll
-  for (int k = 0; k < G::CHUNKS; ++k) {
-    qcut_u4 v = {0u, 0u, 0u, 0u};
-    if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
-    if constexpr (NB == 8) {
-      a[0][2 * k] = v.x; a[1][2 * k] = v.y;
-      a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
-    } else {
-      a[0][4 * k] = v.x; a[0][4 * k + 1] = v.y; a[0][4 * k + 2] = v.z; a[0][4 * k + 3] = v.w;
+    for (int g = 0; g < 2; ++g) {
+      // 16 consecutive shots = 16 * NB contiguous bytes = NB 16-byte loads -> 4 * NB words
+      uint32_t w[4 * NB + 1];
+      const bool valid = FULL || (g * 32 + lane) * 16 < n;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        qcut_u4 v = {0u, 0u, 0u, 0u};
+        if (valid) v = src.obs16_shared_sectors((g * 32 + lane) * 16 * NB + c * 16);
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+      }
+      w[4 * NB] = 0;
+      // cut the rows out: word b of shot r starts at byte r * NB + 4 * b of the group
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+#pragma unroll
+        for (int blk = 0; blk < G::BLOCKS; ++blk) {
+          const int o = r * NB + 4 * blk;
+          const int wi = o >> 2, sh = o & 3;
+          a[blk][16 * g + r] = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], 0x3210 + 0x1111 * sh);
+        }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < G::CHUNKS; ++k) {
+      qcut_u4 v = {0u, 0u, 0u, 0u};
+      if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
+      if constexpr (NB == 8) {
+        a[0][2 * k] = v.x; a[1][2 * k] = v.y;
+        a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
+      } else {
+        a[0][4 * k] = v.x; a[0][4 * k + 1] = v.y; a[0][4 * k + 2] = v.z; a[0][4 * k + 3] = v.w;
+      }
     }
   }
 }
@@ -237,7 +277,15 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
 template <int NB, bool FULL, class Src>
 QCUT_DEV void qcut_qpd_loads(const Src src, int n, int lane, uint32_t* qraw) {
   typedef QcutGeo<NB> G;
-  if constexpr (NB == 1) {
+  if constexpr (G::GROUPED) {
+    // group g: the 16 qpd bytes of shots 16*(32g+lane) .. +15 -> words 4g .. 4g+3 (rows 16g+4w .. +3)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      qcut_u4 v = {0u, 0u, 0u, 0u};
+      if (FULL || (g * 32 + lane) * 16 < n) v = src.qpd16((g * 32 + lane) * 16);
+      qraw[4 * g] = v.x; qraw[4 * g + 1] = v.y; qraw[4 * g + 2] = v.z; qraw[4 * g + 3] = v.w;
+    }
+  } else if constexpr (NB == 1) {
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
       qcut_u4 v = {0u, 0u, 0u, 0u};
@@ -429,6 +477,49 @@ QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long lo
     if (t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
   }
 }
+// ---- direct (HBM -> registers) tile loop with L2 prefetch one step ahead (device only) ---------------
+// cp.async.bulk.prefetch.L2 costs no registers and no shared memory: while the warp works on step s,
+// the copy engine pulls the bytes of step s+1 (or of the first step of the warp's next tile) into L2,
+// so the LDG.128 of the next step are L2 hits instead of HBM round trips.
+QCUT_DEV void qcut_prefetch_l2(const uint8_t* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+
+template <int NB>
+QCUT_DEV void qcut_prefetch_step(const uint8_t* obs_s, const uint8_t* qpd_s, int nbq, int n) {
+  if (n <= 0) return;
+  qcut_prefetch_l2(obs_s, ((uint32_t)n * NB + 15u) & ~15u);
+  qcut_prefetch_l2(qpd_s, ((uint32_t)n * (uint32_t)nbq + 15u) & ~15u);
+}
+
+// Same contract as qcut_lane_tile; (next_obs, next_qpd, next_nbq, next_n) describe the first step of
+// the warp's next tile (next_n = 0: none).
+template <int NB, class Terms>
+QCUT_DEV void qcut_lane_tile_pf(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns,
+                                int lane, uint32_t* acc, const uint8_t* next_obs, const uint8_t* next_qpd,
+                                int next_nbq, int next_n) {
+  typedef QcutGeo<NB> G;
+#pragma unroll
+  for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+  for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    if (lane == 0) {
+      const int rest = ns - s0 - G::STEP_SHOTS;
+      if (rest > 0)
+        qcut_prefetch_step<NB>(obs + (uint64_t)(s0 + G::STEP_SHOTS) * NB, qpd + (uint64_t)(s0 + G::STEP_SHOTS) * nbq, nbq,
+                               rest < G::STEP_SHOTS ? rest : G::STEP_SHOTS);
+      else
+        qcut_prefetch_step<NB>(next_obs, next_qpd, next_nbq, next_n < G::STEP_SHOTS ? next_n : G::STEP_SHOTS);
+    }
+    uint32_t a[G::BLOCKS][32];
+    uint32_t qp[G::BATCHES];
+    qcut_step_any<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
+#pragma unroll
+    for (int u = 0; u < G::BATCHES; ++u)
+      Terms::run(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], acc);
+  }
+}
+
 // ---- bulk-copy staged stream of steps (device only) ---------------------------------------------
 // One staging buffer and one mbarrier per warp.  While the warp does the arithmetic of step s, the
 // copy engine brings step s+1 (possibly the first step of the warp's next tile) into the buffer:
@@ -463,7 +554,7 @@ template <int NB>
 struct QcutStage {
   static const int OBS_BYTES = QcutGeo<NB>::STEP_SHOTS * NB;
   static const int QPD_BYTES = QcutGeo<NB>::STEP_SHOTS;      // staged only when nb_qpd == 1
-  static const int BYTES = OBS_BYTES + QPD_BYTES;            // 9216 / 5120 / 6144 / 8192 for NB = 8 / 4 / 2 / 1
+  static const int BYTES = OBS_BYTES + QPD_BYTES;            // e.g. 9216 / 5120 / 6144 / 8192 for NB = 8 / 4 / 2 / 1
 };
 
 // Issue the bulk copies of one step (lane 0 only).  Sizes are rounded up to 16 bytes: every matrix is

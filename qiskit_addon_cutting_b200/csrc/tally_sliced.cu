@@ -82,14 +82,18 @@ tally_sliced_rt_kernel(const uint8_t* __restrict__ data, const qcut_pub_desc* __
     switch (grp.nb_obs) {
       case 1: rt_tile<1>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
       case 2: rt_tile<2>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
+      case 3: rt_tile<3>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
       case 4: rt_tile<4>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
+      case 5: rt_tile<5>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
+      case 6: rt_tile<6>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
+      case 7: rt_tile<7>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
       case 8: rt_tile<8>(obs, qpd, nbq, ns, lane, mw, nw, T, s_planes, tally); break;
       default: break;  // plan_create never routes other widths here
     }
   }
 }
 
-bool sliced_rt_supports(uint32_t nb_obs) { return nb_obs == 1 || nb_obs == 2 || nb_obs == 4 || nb_obs == 8; }
+bool sliced_rt_supports(uint32_t nb_obs) { return nb_obs >= 1 && nb_obs <= 8; }
 
 int launch_tally_sliced_rt(const qcut_plan* plan, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
                            const TileEntry* d_tiles, int64_t n_tiles, int64_t* d_tallies, cudaStream_t stream) {

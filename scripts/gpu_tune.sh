@@ -16,9 +16,7 @@ except Exception as e:
     print("$name: failed", e); print(open("$OUT/tune_$name.err").read()[-600:])
 PY
 }
-FLAGS=0 run direct_256x2 QCUT_JIT_THREADS=256 QCUT_JIT_MINBLOCKS=2
-FLAGS=4 run staged_256x2 QCUT_JIT_THREADS=256 QCUT_JIT_MINBLOCKS=2
-FLAGS=0 run direct_128x4 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=4
-FLAGS=0 run direct_128x3 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=3
-WL=cfg3_wide_dense SCALE=1 FLAGS=0 run dense_direct QCUT_JIT_THREADS=256 QCUT_JIT_MINBLOCKS=2
-WL=cfg3_wide_dense SCALE=1 FLAGS=0 run dense_direct_128x3 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=3
+FLAGS=0 run direct_pf0 QCUT_JIT_PREFETCH=0
+FLAGS=0 run direct_pf1 QCUT_JIT_PREFETCH=1
+FLAGS=0 run direct_pf2 QCUT_JIT_PREFETCH=2
+FLAGS=0 run direct_pf0_128x4 QCUT_JIT_PREFETCH=0 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=4

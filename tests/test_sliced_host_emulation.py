@@ -43,7 +43,7 @@ def test_emulated_sliced_kernel_matches_oracle_on_golden_cases(lib, name, engine
             assert np.array_equal(got[sl], want[sl]), (name, p)
 
 
-@pytest.mark.parametrize("nbits,qbits", [(5, 3), (13, 1), (27, 2), (64, 5), (8, 12), (61, 20)])
+@pytest.mark.parametrize("nbits,qbits", [(5, 3), (13, 1), (20, 1), (27, 2), (35, 8), (44, 3), (53, 1), (64, 5), (8, 12), (61, 20)])
 @pytest.mark.parametrize("shots", [1, 31, 1024, 4097, 6200])
 def test_emulated_sliced_kernel_widths_and_tails(lib, nbits, qbits, shots):
     """Every covered row width x qpd width, with tile/step boundaries: full steps, ragged tails, multi-tile."""
@@ -54,7 +54,7 @@ def test_emulated_sliced_kernel_widths_and_tails(lib, nbits, qbits, shots):
     tables, data, want = _stage_host(results, coefficients, observables)
     for engine_kind in ("jit", "rt"):
         got, covered = _host_emu.emulate_tallies(tables, data, engine_kind)
-        assert covered.all(), "1/2/4/8-byte rows must be covered by the bit-sliced kernels"
+        assert covered.all(), "rows of 1..8 bytes must be covered by the bit-sliced kernels"
         assert np.array_equal(got, want), engine_kind
 
 
@@ -74,10 +74,10 @@ def test_nvrtc_compiles_golden_plans_for_sm100a(lib):
 
 def test_unsupported_widths_are_not_specialised(lib):
     groups = np.zeros(3, dtype=_lib.GROUP_DTYPE)
-    groups[0] = (2, 3, 0, 0)     # 3-byte rows
-    groups[1] = (2, 8, 6, 0)     # 8-byte rows
-    groups[2] = (2, 16, 22, 0)   # 16-byte rows
-    masks = np.arange(54, dtype=np.uint8)
+    groups[0] = (2, 9, 0, 0)     # 9-byte rows
+    groups[1] = (2, 8, 18, 0)    # 8-byte rows
+    groups[2] = (2, 16, 34, 0)   # 16-byte rows
+    masks = np.arange(66, dtype=np.uint8)
     assert _lib.generate_source(groups, masks, 0) == ""
     assert "struct Terms" in _lib.generate_source(groups, masks, 1)
     assert _lib.generate_source(groups, masks, 2) == ""

@@ -169,6 +169,15 @@ int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_p
 int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,
                      int64_t n_arrays, void* h_dst, int n_threads);
 
+/* Pipelined version of the above for the end-to-end path: worker threads gather runs of arrays into
+ * slots of a (small) pinned buffer and queue one H2D copy per slot on `stream`, so the host-side
+ * gather overlaps the PCIe transfer and only pinned_bytes (e.g. 256 MiB) of pinned memory is needed
+ * whatever the problem size.  Arrays must be sorted by h_dst_offset; d_dst + h_dst_offset[i] receives
+ * array i.  Returns when every byte has left host memory (the copies may still be in flight). */
+int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,
+                   int64_t n_arrays, void* h_pinned, size_t pinned_bytes, uint8_t* d_dst, int n_threads,
+                   void* stream);
+
 /* ---- host-only helpers (no GPU needed): inspection and CPU-side testing of the specialisation -----
  * qcut_generate_source: the CUDA translation unit NVRTC receives when group `group` of this table
  * is specialised.  Returns the length needed including the NUL; 0 if the group cannot be

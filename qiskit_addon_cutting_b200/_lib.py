@@ -95,11 +95,27 @@ SIGNATURES = {
     "qcut_quasi_launch": (_INT, [_VP, _I64, _VP, _VP, _VP, _VP, _INT, _VP, _INT, _VP, _VP, _VP]),
     "qcut_reduce_expvals_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
     "qcut_gather_host": (_INT, [_VP, _VP, _VP, _I64, _VP, _INT]),
+    "qcut_stage_h2d": (_INT, [_VP, _VP, _VP, _I64, _VP, _SZ, _VP, _INT, _VP]),
     "qcut_generate_source": (_SZ, [_VP, _INT, _VP, _SZ, _INT, C.c_char_p, _SZ]),
     "qcut_compile_source": (_INT, [C.c_char_p, C.POINTER(_SZ), _VP, _SZ]),
 }
 
 _lib = None
+_pyhelper = None
+
+
+def load_pyhelper():
+    """The CPython-side result walker (``csrc/pyhelper.c``), loaded with the GIL held."""
+    global _pyhelper
+    if _pyhelper is None:
+        path = PACKAGE_DIR / "_qcut_pyhelper.so"
+        if not path.exists():
+            raise ImportError(f"{path} not found: run `make -C qiskit_addon_cutting_b200/csrc`.")
+        lib = C.PyDLL(str(path))
+        lib.qcut_py_collect.restype = C.c_int64
+        lib.qcut_py_collect.argtypes = [C.py_object, C.c_int64, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, C.py_object]
+        _pyhelper = lib
+    return _pyhelper
 
 
 def load() -> C.CDLL:

@@ -345,4 +345,85 @@ int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const ui
   return QCUT_OK;
 }
 
+int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,
+                   int64_t n_arrays, void* h_pinned, size_t pinned_bytes, uint8_t* d_dst, int n_threads,
+                   void* stream) {
+  if (n_arrays < 0 || (n_arrays > 0 && (!h_src || !h_bytes || !h_dst_offset || !h_pinned || !d_dst)))
+    return set_error("qcut_stage_h2d: bad argument"), QCUT_ERR_INVALID;
+  if (n_arrays == 0) return QCUT_OK;
+  for (int64_t i = 1; i < n_arrays; ++i)
+    if (h_dst_offset[i] < h_dst_offset[i - 1] + h_bytes[i - 1])
+      return set_error("qcut_stage_h2d: arrays must be sorted by destination offset and must not overlap"), QCUT_ERR_INVALID;
+  if (n_threads <= 0) n_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  size_t slot_bytes = (pinned_bytes / (size_t)n_threads) & ~(size_t)255;
+  while (n_threads > 1 && slot_bytes < ((size_t)1 << 20)) {
+    --n_threads;
+    slot_bytes = (pinned_bytes / (size_t)n_threads) & ~(size_t)255;
+  }
+  if (slot_bytes < 4096) return set_error("qcut_stage_h2d: pinned staging buffer too small"), QCUT_ERR_INVALID;
+
+  // Cut the array list into chunks whose destination span fits one staging slot.
+  struct Chunk { int64_t first, last; uint64_t base, span; };
+  std::vector<Chunk> chunks;
+  for (int64_t i = 0; i < n_arrays;) {
+    Chunk c{i, i, h_dst_offset[i], h_bytes[i]};
+    int64_t j = i + 1;
+    while (j < n_arrays && h_dst_offset[j] + h_bytes[j] - c.base <= slot_bytes) {
+      c.span = h_dst_offset[j] + h_bytes[j] - c.base;
+      c.last = j++;
+    }
+    chunks.push_back(c);
+    i = j;
+  }
+  int device = 0;
+  QCUT_CUDA(cudaGetDevice(&device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::atomic<int64_t> next{0};
+  std::atomic<int> failed{0};
+  std::vector<std::string> errors((size_t)n_threads);
+  auto worker = [&](int tid) {
+    if (cudaSetDevice(device) != cudaSuccess) { failed = 1; errors[tid] = "cudaSetDevice failed in staging thread"; return; }
+    char* slot = static_cast<char*>(h_pinned) + (size_t)tid * slot_bytes;
+    cudaEvent_t done = nullptr;
+    if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) { failed = 1; errors[tid] = "cudaEventCreate failed"; return; }
+    bool in_flight = false;
+    for (;;) {
+      const int64_t ci = next.fetch_add(1);
+      if (ci >= (int64_t)chunks.size() || failed.load()) break;
+      const Chunk& c = chunks[(size_t)ci];
+      cudaError_t err = cudaSuccess;
+      if (c.span > slot_bytes) {
+        // a single array larger than a slot: let the driver stage it (rare: > pinned_bytes / n_threads)
+        err = cudaMemcpyAsync(d_dst + c.base, h_src[c.first], h_bytes[c.first], cudaMemcpyHostToDevice, s);
+      } else {
+        if (in_flight) err = cudaEventSynchronize(done);  // the slot's previous H2D has left the staging memory
+        if (err == cudaSuccess) {
+          for (int64_t i = c.first; i <= c.last; ++i)
+            if (h_bytes[i]) std::memcpy(slot + (h_dst_offset[i] - c.base), h_src[i], h_bytes[i]);
+          err = cudaMemcpyAsync(d_dst + c.base, slot, c.span, cudaMemcpyHostToDevice, s);
+        }
+        if (err == cudaSuccess) err = cudaEventRecord(done, s);
+        in_flight = true;
+      }
+      if (err != cudaSuccess) {
+        failed = 1;
+        errors[tid] = std::string("qcut_stage_h2d: ") + cudaGetErrorName(err) + " (" + cudaGetErrorString(err) + ")";
+        break;
+      }
+    }
+    if (in_flight) cudaEventSynchronize(done);
+    cudaEventDestroy(done);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : pool) th.join();
+  if (failed.load()) {
+    for (const auto& e : errors)
+      if (!e.empty()) return set_error(e), QCUT_ERR_CUDA;
+    return set_error("qcut_stage_h2d failed"), QCUT_ERR_CUDA;
+  }
+  return QCUT_OK;
+}
+
 }  // extern "C"

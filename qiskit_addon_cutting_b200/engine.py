@@ -311,87 +311,145 @@ def _pinned_buffer(nbytes: int) -> torch.Tensor:
     return buf
 
 
-def _pub_arrays(pub) -> tuple[np.ndarray, np.ndarray]:
-    data = pub.data
-    obs = data.observable_measurements.array
-    qpd = data.qpd_measurements.array
-    if obs.ndim != 2 or qpd.ndim != 2:
-        raise ValueError("Only PUBs of shape () are supported: BitArray.array must be (num_shots, num_bytes).")
-    shots = qpd.shape[0]
-    if obs.shape[0] < shots:
-        # the reference indexes obs_array[j] for j < qpd_array.shape[0] (cutting_reconstruction.py:155-157)
-        raise IndexError(
-            f"index {obs.shape[0]} is out of bounds for axis 0 with size {obs.shape[0]}"
+def _collect_label(result, lo: int, hi: int):
+    """Arrays of PUBs ``lo .. hi-1`` of one subsystem: (keepalive list, obs ptr, qpd ptr, shots, nb_obs, nb_qpd).
+
+    The attribute walk ``result[idx].data.<register>.array`` and the address / shape of every array are
+    read through the C API (``csrc/pyhelper.c``); arrays that are not C-contiguous ``uint8`` matrices, or
+    whose row counts differ, take the per-PUB Python path below.
+    """
+    n = hi - lo
+    keep: list = []
+    obs_ptr = np.zeros(n, dtype=np.uint64)
+    qpd_ptr = np.zeros(n, dtype=np.uint64)
+    shots = np.zeros(n, dtype=np.int64)
+    nb_obs = np.zeros(n, dtype=np.int64)
+    nb_qpd = np.zeros(n, dtype=np.int64)
+    flags = np.zeros(n, dtype=np.uint8)
+    if n:
+        got = _lib.load_pyhelper().qcut_py_collect(
+            result, lo, hi, obs_ptr.ctypes.data, qpd_ptr.ctypes.data, shots.ctypes.data, nb_obs.ctypes.data,
+            nb_qpd.ctypes.data, flags.ctypes.data, keep,
         )
-    if obs.shape[0] != shots:
-        obs = obs[:shots]
-    if obs.dtype != np.uint8 or not obs.flags.c_contiguous:
-        obs = np.ascontiguousarray(obs, dtype=np.uint8)
-    if qpd.dtype != np.uint8 or not qpd.flags.c_contiguous:
-        qpd = np.ascontiguousarray(qpd, dtype=np.uint8)
-    return obs, qpd
+        if got != n:
+            raise RuntimeError("qcut_py_collect failed")
+    u8 = np.dtype(np.uint8)
+    for j in np.flatnonzero(flags):
+        o, q = np.asarray(keep[2 * j]), np.asarray(keep[2 * j + 1])
+        if o.ndim != 2 or q.ndim != 2:
+            raise ValueError("Only PUBs of shape () are supported: BitArray.array must be (num_shots, num_bytes).")
+        s = q.shape[0]
+        if o.shape[0] < s:
+            # the reference indexes obs_array[j] for j < qpd_array.shape[0] (cutting_reconstruction.py:155-157)
+            raise IndexError(f"index {o.shape[0]} is out of bounds for axis 0 with size {o.shape[0]}")
+        o = np.ascontiguousarray(o[:s], dtype=u8)
+        q = np.ascontiguousarray(q, dtype=u8)
+        keep[2 * j], keep[2 * j + 1] = o, q
+        obs_ptr[j], qpd_ptr[j] = o.ctypes.data, q.ctypes.data
+        shots[j], nb_obs[j], nb_qpd[j] = s, o.shape[1], q.shape[1]
+    return keep, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd
+
+
+@dataclass
+class HostArrays:
+    """Borrowed shot buffers of a call, as flat address tables (obs_0, qpd_0, obs_1, qpd_1, ...)."""
+
+    keep: list  # the array objects: keeps the addresses valid
+    src: np.ndarray  # uint64 host addresses
+    nbytes: np.ndarray  # uint64 sizes
+    dst: np.ndarray  # uint64 offsets in the staged buffer
+
+    def __len__(self) -> int:
+        return len(self.src)
 
 
 def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int,
-                      n_obs: int) -> tuple[HostTables, list[np.ndarray]]:
+                      n_obs: int) -> tuple[HostTables, HostArrays]:
     """Walk the PUBs of coefficient range ``[i_lo, i_hi)`` of every label (host only, no device).
 
-    Returns the tables and the borrowed ``[obs_0, qpd_0, obs_1, qpd_1, ...]`` arrays in PUB order.
+    Offsets, tally slots and group variants are computed with NumPy, not per PUB.
     """
     builder = TableBuilder(n_obs)
-    arrays: list[np.ndarray] = []
-    pub_rows = []
+    keep_all: list = []
+    src_chunks, nbytes_chunks, dst_chunks, chunks = [], [], [], []
     offset = 0
     tally_offset = 0
+    n_pubs = 0
     for result, collection in zip(results_by_label, collections):
         n_groups = len(collection.groups)
-        li = builder.add_label(collection, len(pub_rows))
-        for i in range(i_lo, i_hi):
-            for g in range(n_groups):
-                obs, qpd = _pub_arrays(result[i * n_groups + g])
-                shots, nb_obs = obs.shape
-                nb_qpd = qpd.shape[1]
-                obs_off = offset
-                offset += _align(shots * nb_obs)
-                qpd_off = offset
-                offset += _align(shots * nb_qpd)
-                arrays.append(obs)
-                arrays.append(qpd)
-                pub_rows.append(
-                    (obs_off, qpd_off, tally_offset, shots, builder.group_variant(li, g, nb_obs), nb_qpd, 0)
-                )
-                tally_offset += builder.n_terms(li, g)
-    pubs = np.array(pub_rows, dtype=PUB_DTYPE) if pub_rows else np.zeros(0, dtype=PUB_DTYPE)
-    if len(pubs) and int(pubs["shots"].max()) >= 2**31:
-        raise ValueError("A PUB with 2**31 or more shots is not supported.")
+        li = builder.add_label(collection, n_pubs)
+        keep, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd = _collect_label(result, i_lo * n_groups, i_hi * n_groups)
+        n = len(shots)
+        g_idx = np.tile(np.arange(n_groups), i_hi - i_lo) if n else np.zeros(0, dtype=np.int64)
+        # group variants: one per distinct (group, row width)
+        variant = np.empty(n, dtype=np.uint32)
+        for g, nb in {(int(g), int(nb)) for g, nb in zip(g_idx.tolist(), nb_obs.tolist())}:
+            variant[(g_idx == g) & (nb_obs == nb)] = builder.group_variant(li, g, nb)
+        terms = np.array([builder.n_terms(li, g) for g in range(n_groups)], dtype=np.int64)[g_idx] if n else np.zeros(0, dtype=np.int64)
+        raw = np.empty(2 * n, dtype=np.int64)
+        raw[0::2] = shots * nb_obs
+        raw[1::2] = shots * nb_qpd
+        sizes = (raw + _ALIGN - 1) // _ALIGN * _ALIGN
+        starts = offset + np.concatenate([[0], np.cumsum(sizes)[:-1]]) if n else np.zeros(0, dtype=np.int64)
+        pubs = np.zeros(n, dtype=PUB_DTYPE)
+        pubs["obs_offset"] = starts[0::2]
+        pubs["qpd_offset"] = starts[1::2]
+        pubs["tally_offset"] = tally_offset + (np.concatenate([[0], np.cumsum(terms)[:-1]]) if n else 0)
+        pubs["shots"] = shots
+        pubs["group"] = variant
+        pubs["nb_qpd"] = nb_qpd
+        if n and int(shots.max()) >= 2**31:
+            raise ValueError("A PUB with 2**31 or more shots is not supported.")
+        src = np.empty(2 * n, dtype=np.uint64)
+        src[0::2] = obs_ptr
+        src[1::2] = qpd_ptr
+        src_chunks.append(src)
+        nbytes_chunks.append(raw.astype(np.uint64))
+        dst_chunks.append(starts.astype(np.uint64))
+        offset += int(sizes.sum())
+        tally_offset += int(terms.sum())
+        n_pubs += n
+        chunks.append(pubs)
+        keep_all.extend(keep)
+    pubs = np.concatenate(chunks) if chunks else np.zeros(0, dtype=PUB_DTYPE)
+    cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint64)  # noqa: E731
+    arrays = HostArrays(keep_all, cat(src_chunks), cat(nbytes_chunks), cat(dst_chunks))
     return builder.tables(pubs, coeffs[i_lo:i_hi], tally_offset, max(offset, _ALIGN)), arrays
 
 
-def gather_arrays(tables: HostTables, arrays: list[np.ndarray], dst_ptr: int, n_threads: int = 0) -> None:
+def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_threads: int = 0) -> None:
     """Copy every borrowed buffer to its offset in the staging buffer at ``dst_ptr`` (threads in C)."""
-    n = len(arrays)
-    if n == 0:
+    if len(arrays) == 0:
         return
-    src = np.fromiter((a.ctypes.data for a in arrays), dtype=np.uint64, count=n)
-    nbytes = np.fromiter((a.nbytes for a in arrays), dtype=np.uint64, count=n)
-    dst = np.empty(n, dtype=np.uint64)
-    dst[0::2] = tables.pubs["obs_offset"]
-    dst[1::2] = tables.pubs["qpd_offset"]
     check(
-        _lib.load().qcut_gather_host(_lib.np_ptr(src), _lib.np_ptr(nbytes), _lib.np_ptr(dst), n, dst_ptr, n_threads),
+        _lib.load().qcut_gather_host(
+            _lib.np_ptr(arrays.src), _lib.np_ptr(arrays.nbytes), _lib.np_ptr(arrays.dst), len(arrays), dst_ptr, n_threads
+        ),
         "qcut_gather_host",
     )
 
 
+_STAGING_BYTES = 256 << 20  # pinned staging ring for the end-to-end path, independent of the problem size
+
+
 def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
              *, flags: int = 0) -> DeviceBatch:
-    """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM."""
+    """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM.
+
+    Worker threads gather runs of borrowed ``BitArray`` buffers into a small pinned ring and queue one H2D
+    copy per run on the current stream (``qcut_stage_h2d``): the host gather overlaps the PCIe transfer.
+    """
     _lib.require_device()
     tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs)
-    # Gather every borrowed buffer into one pinned staging buffer (threads), then one H2D copy.
     total = tables.data_bytes
-    pinned = _pinned_buffer(total)
-    gather_arrays(tables, arrays, pinned.data_ptr())
     data = torch.empty(total, dtype=torch.uint8, device="cuda")
-    data.copy_(pinned[:total], non_blocking=True)
+    if len(arrays):
+        pinned = _pinned_buffer(_STAGING_BYTES)
+        check(
+            _lib.load().qcut_stage_h2d(
+                _lib.np_ptr(arrays.src), _lib.np_ptr(arrays.nbytes), _lib.np_ptr(arrays.dst), len(arrays),
+                pinned.data_ptr(), pinned.numel(), data.data_ptr(), 0, _stream_ptr(),
+            ),
+            "qcut_stage_h2d",
+        )
     return DeviceBatch(tables, data, flags=flags)

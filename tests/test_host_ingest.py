@@ -1,0 +1,59 @@
+"""Host-side ingestion (no GPU): the C-API result walk, table building and gather reproduce the staged layout."""
+
+import numpy as np
+import pytest
+
+import _cases
+from oracle import c_oracle, oracle
+from qiskit_addon_cutting_b200 import engine
+from qiskit_addon_cutting_b200.containers import BitArray, DataBin, PauliList, PrimitiveResult, PubResult, WeightType
+from qiskit_addon_cutting_b200.observable_grouping import ObservableCollection
+
+
+def _tables(results, coefficients, observables):
+    labels = list(observables)
+    colls = [ObservableCollection(observables[label]) for label in labels]
+    coeffs = np.array([c for c, _ in coefficients], dtype=np.float64)
+    return engine.build_host_tables([results[label] for label in labels], colls, coeffs, 0, len(coeffs),
+                                    len(observables[labels[0]]))
+
+
+@pytest.mark.parametrize("name", ["molecular", "odd_widths", "heavy_hex"])
+def test_staged_layout_feeds_the_c_oracle(lib, name):
+    """tables + gathered bytes are self-consistent: the C oracle run on them gives the oracle's tallies."""
+    results, coefficients, observables = _cases.SMALL_CASES[name]()
+    tables, arrays = _tables(results, coefficients, observables)
+    data = np.zeros(tables.data_bytes, dtype=np.uint8)
+    engine.gather_arrays(tables, arrays, data.ctypes.data, 3)
+    _, tally = c_oracle.pubs(data, tables.pubs, tables.groups, tables.masks, tables.n_tallies, want_seq=False, n_threads=2)
+    want = np.concatenate([t for label in observables for t in oracle.all_tallies(results, coefficients, observables)[label]])
+    assert np.array_equal(tally, want)
+    assert tables.single_slot and tables.work == int((tables.pubs["shots"] * tables.groups["n_terms"][tables.pubs["group"]]).sum())
+
+
+def test_non_conforming_arrays_take_the_slow_path(lib):
+    """Fortran-ordered / strided / wider-than-needed arrays are copied to C-contiguous uint8 rows first."""
+    rng = np.random.default_rng(3)
+    observables = {"A": PauliList(["ZIZ", "IZZ", "ZZZ"])}
+    base = rng.integers(0, 8, size=(40, 1), dtype=np.uint8)
+    qpd = rng.integers(0, 4, size=(33, 1), dtype=np.uint8)
+
+    class Reg:  # a register whose .array is not a plain C-contiguous matrix
+        def __init__(self, array):
+            self.array = array
+
+    strided = np.asfortranarray(np.repeat(base, 2, axis=1))[:, :1]  # not C-contiguous, 40 rows (> 33 qpd rows)
+    results = {"A": PrimitiveResult([PubResult(DataBin(observable_measurements=Reg(strided), qpd_measurements=Reg(qpd)))])}
+    coefficients = [(1.0, WeightType.EXACT)]
+    tables, arrays = _tables(results, coefficients, observables)
+    assert int(tables.pubs["shots"][0]) == 33  # shots come from the qpd register (reference :155)
+    data = np.zeros(tables.data_bytes, dtype=np.uint8)
+    engine.gather_arrays(tables, arrays, data.ctypes.data, 1)
+    _, tally = c_oracle.pubs(data, tables.pubs, tables.groups, tables.masks, tables.n_tallies, want_seq=False)
+    ref = {"A": PrimitiveResult([PubResult(DataBin(observable_measurements=BitArray(np.ascontiguousarray(base[:33]), 3),
+                                                   qpd_measurements=BitArray(qpd, 2)))])}
+    assert np.array_equal(tally, oracle.all_tallies(ref, coefficients, observables)["A"][0])
+    # fewer observable rows than qpd rows: the reference raises IndexError (obs_array[j])
+    short = {"A": PrimitiveResult([PubResult(DataBin(observable_measurements=Reg(base[:10]), qpd_measurements=Reg(qpd)))])}
+    with pytest.raises(IndexError):
+        _tables(short, coefficients, observables)

@@ -25,8 +25,8 @@ colls = w.collections(); coeffs = w.coefficients()[:w.n_coeffs]
 lst = [res[l] for l in w.observables]
 for rep in range(2):
     t0 = time.perf_counter(); tables, arrays = engine.build_host_tables(lst, colls, coeffs, 0, w.n_coeffs, w.n_obs); t1 = time.perf_counter()
-    src, nb = engine._array_pointers(arrays); t2 = time.perf_counter()
+    t2 = time.perf_counter()
     batch = engine.stage_v2(lst, colls, coeffs, 0, w.n_coeffs, w.n_obs); torch.cuda.synchronize(); t3 = time.perf_counter()
     out = batch.run(); torch.cuda.synchronize(); t4 = time.perf_counter()
-    print(f"rep {rep}: tables {t1-t0:.3f}s pointers {t2-t1:.3f}s stage_v2(total incl. tables) {t3-t2:.3f}s kernels {t4-t3:.4f}s")
+    print(f"rep {rep}: tables+pointers {t1-t0:.3f}s stage_v2(total incl. tables) {t3-t2:.3f}s kernels {t4-t3:.4f}s")
 PY

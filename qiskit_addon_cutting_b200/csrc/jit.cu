@@ -57,12 +57,15 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   os << "    (void)Q;\n";
   for (uint32_t t = 0; t < T; ++t) {
     const uint8_t* row = masks + gd.mask_offset + (size_t)t * nb;
-    os << "    acc[" << t / 4 << "] += (uint32_t)__popc(qp";
+    // term t lives in field t / NACC of packed register t % NACC: consecutive terms touch different
+    // registers, so their popcount -> add chains are independent
+    const uint32_t nacc = (T + 3) / 4;
+    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(qp";
     for (uint32_t byte = 0; byte < nb; ++byte)
       for (uint32_t bit = 0; bit < 8; ++bit)
         if ((row[byte] >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
     os << ")";
-    if (t % 4) os << " << " << 8 * (t % 4);
+    if (t / nacc) os << " << " << 8 * (t / nacc);
     os << ";\n";
   }
   os << "  }\n};\n\n";
@@ -150,7 +153,7 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
         "                                  uint32_t* odd_out) {\n"
         "  uint32_t acc[Terms::NACC];\n"
         "  qcut_lane_tile<Terms::NB, Terms>(obs, qpd, nbq, ns, lane, acc);\n"
-        "  for (int t = 0; t < Terms::T; ++t) odd_out[t] = (acc[t / 4] >> (8 * (t % 4))) & 0xFFu;\n"
+        "  for (int t = 0; t < Terms::T; ++t) odd_out[t] = (acc[t % Terms::NACC] >> (8 * (t / Terms::NACC))) & 0xFFu;\n"
         "  return Terms::T;\n"
         "}\n"
         "// run-time-mask engine, one lane of one tile (planes parked in a per-lane column)\n"

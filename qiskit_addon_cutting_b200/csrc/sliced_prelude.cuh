@@ -453,28 +453,32 @@ QCUT_DEV void qcut_red_add(unsigned long long* p, unsigned long long v) {
 }
 
 // Warp-level flush of the packed per-lane counters: tally[t] += ns - 2 * (#odd shots).
-// Branch free: every packed register is widened to two pairs of 16-bit fields (the warp sum is
-// <= 4096) and summed with two REDUX; lane l keeps the totals of terms l, l + 32, l + 64, ... and
-// the warp finishes with ceil(T / 32) coalesced 64-bit reductions to global memory.
+// Term t sits in field t / NACC of register t % NACC (NACC = ceil(T / 4)).  Branch free: every packed
+// register is widened to two pairs of 16-bit fields (the warp sum is <= 4096) and summed with two
+// REDUX; lane l = 4 * (r % 8) + f keeps the total of (register r, field f) for r = l/4, l/4 + 8, ...,
+// and the warp finishes with ceil(NACC / 8) 64-bit reductions to global memory.
 template <int T>
 QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long long* __restrict__ tally) {
-  uint32_t mine[(T + 31) / 32];
+  constexpr int NACC = (T + 3) / 4;
+  uint32_t mine[(NACC + 7) / 8];
 #pragma unroll
-  for (int c = 0; c < (T + 31) / 32; ++c) mine[c] = 0;
-  const bool odd_field = lane & 1;
-  const uint32_t shift = (lane & 2) ? 16u : 0u;
-  const int owner = lane >> 2;  // this lane owns the fields of registers r with r % 8 == owner
+  for (int c = 0; c < (NACC + 7) / 8; ++c) mine[c] = 0;
+  const int field = lane & 3;
+  const bool odd_field = field & 1;
+  const uint32_t shift = (field & 2) ? 16u : 0u;
+  const int owner = lane >> 2;  // this lane owns registers r with r % 8 == owner
 #pragma unroll
-  for (int r = 0; r < (T + 3) / 4; ++r) {
-    const uint32_t ev = __reduce_add_sync(0xffffffffu, acc[r] & 0x00FF00FFu);         // terms 4r, 4r+2
-    const uint32_t od = __reduce_add_sync(0xffffffffu, (acc[r] >> 8) & 0x00FF00FFu);  // terms 4r+1, 4r+3
+  for (int r = 0; r < NACC; ++r) {
+    const uint32_t ev = __reduce_add_sync(0xffffffffu, acc[r] & 0x00FF00FFu);         // fields 0, 2
+    const uint32_t od = __reduce_add_sync(0xffffffffu, (acc[r] >> 8) & 0x00FF00FFu);  // fields 1, 3
     const uint32_t val = ((odd_field ? od : ev) >> shift) & 0xFFFFu;
     if ((r & 7) == owner) mine[r >> 3] = val;
   }
 #pragma unroll
-  for (int c = 0; c < (T + 31) / 32; ++c) {
-    const int t = 32 * c + lane;
-    if (t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
+  for (int c = 0; c < (NACC + 7) / 8; ++c) {
+    const int r = 8 * c + owner;
+    const int t = field * NACC + r;
+    if (r < NACC && t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
   }
 }
 // ---- direct (HBM -> registers) tile loop with L2 prefetch one step ahead (device only) ---------------

@@ -16,7 +16,6 @@ except Exception as e:
     print("$name: failed", e); print(open("$OUT/tune_$name.err").read()[-600:])
 PY
 }
-FLAGS=0 run direct_pf0 QCUT_JIT_PREFETCH=0
-FLAGS=0 run direct_pf1 QCUT_JIT_PREFETCH=1
-FLAGS=0 run direct_pf2 QCUT_JIT_PREFETCH=2
-FLAGS=0 run direct_pf0_128x4 QCUT_JIT_PREFETCH=0 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=4
+FLAGS=0 run direct QCUT_JIT_PREFETCH=0
+WL=cfg3_wide_dense SCALE=1 FLAGS=0 run dense QCUT_JIT_PREFETCH=0
+WL=cfg3_wide_local SCALE=1 FLAGS=0 run local QCUT_JIT_PREFETCH=0

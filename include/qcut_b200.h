@@ -97,9 +97,10 @@ int qcut_device_count(void);
 /* ---- plan ---------------------------------------------------------------------------------------
  * Replaces the per-call host state the reference builds at cutting_reconstruction.py:113-116.
  * Every group is assigned one of the K1 kernels:
- *   0 = generic (any width), 1 = bit-sliced with run-time masks, >= 2 = bit-sliced kernel
- *   specialised by NVRTC for that group's masks (at most QCUT_MAX_JIT_KERNELS per plan, chosen
- *   by term count; the rest use kernel 0/1).
+ *   0 = generic (any width), 1 = bit-sliced with run-time masks, >= 2 = bit-sliced kernels
+ *   specialised by NVRTC for the groups' masks: one kernel per group for the QCUT_MAX_JIT_KERNELS
+ *   groups with the most terms (>= 12), multi-group kernels (one __noinline__ function per group)
+ *   for the other groups with rows of <= 8 bytes; what is left uses kernel 0/1.
  * flags: QCUT_PLAN_NO_JIT disables NVRTC specialisation, QCUT_PLAN_GENERIC_ONLY forces kernel 0. */
 #define QCUT_PLAN_NO_JIT 1u
 #define QCUT_PLAN_GENERIC_ONLY 2u
@@ -186,6 +187,10 @@ int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint
 size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
                             size_t mask_bytes, int group, char* buf, size_t buf_len);
 int qcut_compile_source(const char* source, size_t* cubin_bytes, char* cubin_buf, size_t cubin_buf_len);
+/* Runs the kernel assignment and every NVRTC compilation qcut_plan_create would run for these groups,
+ * without touching a device; returns the number of specialised kernels and their total cubin size. */
+int qcut_plan_compile_check(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
+                            size_t mask_bytes, int* n_kernels, size_t* cubin_bytes);
 
 #ifdef __cplusplus
 }

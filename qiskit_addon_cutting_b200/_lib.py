@@ -98,6 +98,7 @@ SIGNATURES = {
     "qcut_stage_h2d": (_INT, [_VP, _VP, _VP, _I64, _VP, _SZ, _VP, _INT, _VP]),
     "qcut_generate_source": (_SZ, [_VP, _INT, _VP, _SZ, _INT, C.c_char_p, _SZ]),
     "qcut_compile_source": (_INT, [C.c_char_p, C.POINTER(_SZ), _VP, _SZ]),
+    "qcut_plan_compile_check": (_INT, [_VP, _INT, _VP, _SZ, C.POINTER(_INT), C.POINTER(_SZ)]),
 }
 
 _lib = None
@@ -182,3 +183,17 @@ def compile_source(source: str) -> bytes:
     buf = C.create_string_buffer(size.value)
     check(lib.qcut_compile_source(src, C.byref(size), buf, size.value), "qcut_compile_source")
     return buf.raw
+
+
+def plan_compile_check(groups: np.ndarray, masks: np.ndarray) -> tuple[int, int]:
+    """Run every NVRTC compilation a plan for these groups needs (no GPU); returns (#kernels, cubin bytes)."""
+    lib = load()
+    groups = np.ascontiguousarray(groups, dtype=GROUP_DTYPE)
+    masks = np.ascontiguousarray(masks, dtype=np.uint8)
+    n, size = _INT(0), _SZ(0)
+    check(
+        lib.qcut_plan_compile_check(np_ptr(groups), len(groups), np_ptr(masks) if masks.size else None, masks.size,
+                                    C.byref(n), C.byref(size)),
+        "qcut_plan_compile_check",
+    )
+    return n.value, size.value

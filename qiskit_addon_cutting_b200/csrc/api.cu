@@ -38,10 +38,10 @@ int launch_tally_generic(const qcut_plan*, const uint8_t*, const qcut_pub_desc*,
 int launch_tally_sliced_rt(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, const TileEntry*, int64_t,
                            int64_t*, cudaStream_t);
 int launch_tally_jit(const JitKernel&, const uint8_t*, const qcut_pub_desc*, const TileEntry*, int64_t, int64_t*,
-                     cudaStream_t);
+                     const GroupDev*, cudaStream_t);
 bool sliced_rt_supports(uint32_t nb_obs);
 bool jit_supports(const qcut_group_desc& gd);
-int jit_build(qcut_plan* plan);
+int jit_build(qcut_plan* plan, bool load);
 void jit_release(qcut_plan* plan);
 template <typename TallyT>
 int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, int, const uint32_t*,
@@ -53,10 +53,76 @@ int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const ui
 // Groups with at least this many terms are worth an NVRTC specialisation: below it the (shared)
 // load + transposition cost dominates and the run-time-mask kernel is within a few percent.
 constexpr uint32_t kJitMinTerms = 12;
+// Multi-group kernels: distinct mask sets per kernel, and how many such kernels a plan may have
+// (groups beyond that use the run-time-mask kernel).
+constexpr size_t kMultiVariants = 24;
+constexpr size_t kMaxMultiKernels = 32;
 
 }  // namespace qcut
 
 using namespace qcut;
+
+// Decide which K1 kernel serves each group (fills plan->groups_dev[*].kernel / .variant and plan->jit).
+static void assign_jit_kernels(qcut_plan* plan) {
+  const int n_groups = plan->n_groups;
+  const qcut_group_desc* h_groups = plan->groups.data();
+  const uint8_t* h_masks = plan->masks.data();
+  // Pick the groups to specialise: the QCUT_MAX_JIT_KERNELS distinct (width, masks) sets with the
+  // most terms among those with >= kJitMinTerms terms.
+  {
+    std::map<std::string, std::vector<int>> by_masks;
+    for (int g = 0; g < n_groups; ++g) {
+      const qcut_group_desc& gd = h_groups[g];
+      if (gd.n_terms < kJitMinTerms || !jit_supports(gd)) continue;
+      std::string key(reinterpret_cast<const char*>(&gd.nb_obs), sizeof(gd.nb_obs));
+      key.append(reinterpret_cast<const char*>(h_masks + gd.mask_offset), (size_t)gd.n_terms * gd.nb_obs);
+      by_masks[key].push_back(g);
+    }
+    std::vector<const std::vector<int>*> sets;
+    for (const auto& kv : by_masks) sets.push_back(&kv.second);
+    std::stable_sort(sets.begin(), sets.end(), [&](const std::vector<int>* a, const std::vector<int>* b) {
+      return h_groups[a->front()].n_terms > h_groups[b->front()].n_terms;
+    });
+    if (sets.size() > QCUT_MAX_JIT_KERNELS) sets.resize(QCUT_MAX_JIT_KERNELS);
+    std::vector<bool> taken((size_t)n_groups, false);
+    for (const auto* set : sets) {
+      JitKernel jk;
+      jk.group = set->front();
+      for (int g : *set) {
+        plan->groups_dev[g].kernel = KERNEL_JIT0 + (uint32_t)plan->jit.size();
+        taken[(size_t)g] = true;
+      }
+      plan->jit.push_back(std::move(jk));
+    }
+    // Everything else the bit-sliced kernels cover (few terms, or beyond the per-group kernel budget)
+    // goes into multi-group kernels, kMultiVariants distinct mask sets per kernel.
+    std::map<std::string, std::vector<int>> small;
+    std::vector<const std::vector<int>*> small_sets;
+    for (int g = 0; g < n_groups; ++g) {
+      const qcut_group_desc& gd = h_groups[g];
+      if (taken[(size_t)g] || !jit_supports(gd)) continue;
+      std::string key(reinterpret_cast<const char*>(&gd.nb_obs), sizeof(gd.nb_obs));
+      key.append(reinterpret_cast<const char*>(h_masks + gd.mask_offset), (size_t)gd.n_terms * gd.nb_obs);
+      auto ins = small.emplace(std::move(key), std::vector<int>());
+      if (ins.second) small_sets.push_back(&ins.first->second);
+      ins.first->second.push_back(g);
+    }
+    for (size_t first = 0; first < small_sets.size() && plan->jit.size() < (size_t)(QCUT_MAX_JIT_KERNELS + kMaxMultiKernels);
+         first += kMultiVariants) {
+      JitKernel jk;
+      const size_t last = std::min(small_sets.size(), first + kMultiVariants);
+      for (size_t v = first; v < last; ++v) {
+        jk.variants.push_back(small_sets[v]->front());
+        for (int g : *small_sets[v]) {
+          plan->groups_dev[g].kernel = KERNEL_JIT0 + (uint32_t)plan->jit.size();
+          plan->groups_dev[g].variant = (uint32_t)(v - first);
+        }
+      }
+      plan->jit.push_back(std::move(jk));
+    }
+  }
+}
+
 
 extern "C" {
 
@@ -118,30 +184,9 @@ int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_
     }
   }
 
-  // Pick the groups to specialise: the QCUT_MAX_JIT_KERNELS distinct (width, masks) sets with the
-  // most terms among those with >= kJitMinTerms terms.
   if (!(flags & (QCUT_PLAN_NO_JIT | QCUT_PLAN_GENERIC_ONLY))) {
-    std::map<std::string, std::vector<int>> by_masks;
-    for (int g = 0; g < n_groups; ++g) {
-      const qcut_group_desc& gd = h_groups[g];
-      if (gd.n_terms < kJitMinTerms || !jit_supports(gd)) continue;
-      std::string key(reinterpret_cast<const char*>(&gd.nb_obs), sizeof(gd.nb_obs));
-      key.append(reinterpret_cast<const char*>(h_masks + gd.mask_offset), (size_t)gd.n_terms * gd.nb_obs);
-      by_masks[key].push_back(g);
-    }
-    std::vector<const std::vector<int>*> sets;
-    for (const auto& kv : by_masks) sets.push_back(&kv.second);
-    std::stable_sort(sets.begin(), sets.end(), [&](const std::vector<int>* a, const std::vector<int>* b) {
-      return h_groups[a->front()].n_terms > h_groups[b->front()].n_terms;
-    });
-    if (sets.size() > QCUT_MAX_JIT_KERNELS) sets.resize(QCUT_MAX_JIT_KERNELS);
-    for (const auto* set : sets) {
-      JitKernel jk;
-      jk.group = set->front();
-      for (int g : *set) plan->groups_dev[g].kernel = KERNEL_JIT0 + (uint32_t)plan->jit.size();
-      plan->jit.push_back(std::move(jk));
-    }
-    const int rc = jit_build(plan);
+    assign_jit_kernels(plan);
+    const int rc = jit_build(plan, true);
     if (rc != QCUT_OK) {
       qcut_plan_destroy(plan);
       return rc;
@@ -199,7 +244,13 @@ int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int
   if (!plan || n_pubs < 0 || (n_pubs > 0 && !h_pubs)) return set_error("qcut_schedule_create: bad argument"), QCUT_ERR_INVALID;
   if (n_pubs >= (int64_t)1 << 32) return set_error("qcut_schedule_create: more than 2^32 PUBs"), QCUT_ERR_INVALID;
   const int nk = plan->n_kernels();
-  std::vector<int64_t> count(nk + 1, 0);
+  // Tiles are listed kernel by kernel and, inside a kernel, variant by variant (PUB order within).
+  constexpr int64_t kMaxVariants = 64;
+  auto key_of = [&](const qcut_pub_desc& pd) {
+    const GroupDev& gd = plan->groups_dev[pd.group];
+    return (int64_t)gd.kernel * kMaxVariants + std::min<int64_t>(gd.variant, kMaxVariants - 1);
+  };
+  std::vector<int64_t> count((size_t)nk * kMaxVariants + 1, 0);
   for (int64_t p = 0; p < n_pubs; ++p) {
     if (h_pubs[p].group >= (uint32_t)plan->n_groups) {
       set_error("qcut_schedule_create: PUB " + std::to_string(p) + " references group " + std::to_string(h_pubs[p].group) +
@@ -207,19 +258,20 @@ int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int
       return QCUT_ERR_INVALID;
     }
     const int64_t tiles = ((int64_t)h_pubs[p].shots + QCUT_TILE_SHOTS - 1) / QCUT_TILE_SHOTS;
-    count[plan->groups_dev[h_pubs[p].group].kernel + 1] += tiles;
+    count[(size_t)key_of(h_pubs[p]) + 1] += tiles;
   }
-  for (int k = 0; k < nk; ++k) count[k + 1] += count[k];
+  for (size_t k = 0; k + 1 < count.size(); ++k) count[k + 1] += count[k];
   qcut_schedule* sch = new (std::nothrow) qcut_schedule();
   if (!sch) return set_error("qcut_schedule_create: out of host memory"), QCUT_ERR_NOMEM;
   sch->n_pubs = n_pubs;
-  sch->n_tiles = count[nk];
-  sch->kernel_tile_begin = count;
+  sch->n_tiles = count.back();
+  sch->kernel_tile_begin.resize((size_t)nk + 1);
+  for (int k = 0; k <= nk; ++k) sch->kernel_tile_begin[(size_t)k] = count[(size_t)k * kMaxVariants];
   std::vector<TileEntry> tiles((size_t)std::max<int64_t>(sch->n_tiles, 1));
   std::vector<int64_t> cursor(count.begin(), count.end() - 1);
   for (int64_t p = 0; p < n_pubs; ++p) {
     const int64_t n = ((int64_t)h_pubs[p].shots + QCUT_TILE_SHOTS - 1) / QCUT_TILE_SHOTS;
-    int64_t& c = cursor[plan->groups_dev[h_pubs[p].group].kernel];
+    int64_t& c = cursor[(size_t)key_of(h_pubs[p])];
     for (int64_t t = 0; t < n; ++t) tiles[(size_t)c++] = TileEntry{(uint32_t)p, (uint32_t)t};
   }
   auto fail = [&](cudaError_t err, const char* what) {
@@ -276,7 +328,7 @@ int qcut_tally_launch(const qcut_plan* plan, const qcut_schedule* schedule, cons
     int rc;
     if (k == (int)KERNEL_GENERIC) rc = launch_tally_generic(plan, d_data, schedule->d_pubs, tiles, n, d_tallies, s);
     else if (k == (int)KERNEL_SLICED_RT) rc = launch_tally_sliced_rt(plan, d_data, schedule->d_pubs, tiles, n, d_tallies, s);
-    else rc = launch_tally_jit(plan->jit[k - KERNEL_JIT0], d_data, schedule->d_pubs, tiles, n, d_tallies, s);
+    else rc = launch_tally_jit(plan->jit[k - KERNEL_JIT0], d_data, schedule->d_pubs, tiles, n, d_tallies, plan->d_groups, s);
     if (rc != QCUT_OK) return rc;
     ++launches;
   }
@@ -424,6 +476,29 @@ int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint
     return set_error("qcut_stage_h2d failed"), QCUT_ERR_CUDA;
   }
   return QCUT_OK;
+}
+
+int qcut_plan_compile_check(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks, size_t mask_bytes,
+                            int* n_kernels, size_t* cubin_bytes) {
+  if (!h_groups || n_groups <= 0) return set_error("qcut_plan_compile_check: no groups"), QCUT_ERR_INVALID;
+  qcut_plan plan;
+  plan.n_groups = n_groups;
+  plan.groups.assign(h_groups, h_groups + n_groups);
+  if (mask_bytes) plan.masks.assign(h_masks, h_masks + mask_bytes);
+  plan.groups_dev.resize((size_t)n_groups);
+  for (int g = 0; g < n_groups; ++g) {
+    if ((size_t)h_groups[g].mask_offset + (size_t)h_groups[g].n_terms * h_groups[g].nb_obs > mask_bytes)
+      return set_error("qcut_plan_compile_check: masks run past the mask buffer"), QCUT_ERR_INVALID;
+    plan.groups_dev[(size_t)g] = GroupDev{};
+    plan.groups_dev[(size_t)g].kernel = sliced_rt_supports(h_groups[g].nb_obs) ? KERNEL_SLICED_RT : KERNEL_GENERIC;
+  }
+  assign_jit_kernels(&plan);
+  const int rc = jit_build(&plan, false);
+  if (n_kernels) *n_kernels = (int)plan.jit.size();
+  size_t total = 0;
+  for (const JitKernel& jk : plan.jit) total += jk.cubin.size();
+  if (cubin_bytes) *cubin_bytes = total;
+  return rc;
 }
 
 }  // extern "C"

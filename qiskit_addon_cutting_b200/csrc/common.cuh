@@ -18,7 +18,8 @@ struct GroupDev {
   uint32_t n_words;      // ceil(nb_obs / 4): 32-bit words per (zero padded) mask row
   uint32_t word_offset;  // index of the group's first mask word in mask_words[]
   uint32_t kernel;       // 0 = generic, 1 = bit-sliced run-time masks, >= 2 = NVRTC-specialised
-  uint32_t reserved[3];
+  uint32_t variant;      // index of the group's code inside a multi-group specialised kernel
+  uint32_t reserved[2];
 };
 
 struct TileEntry {
@@ -48,7 +49,8 @@ struct JitKernel {
   cudaKernel_t kernel = nullptr;
   int min_blocks = 2;
   int threads = 256;
-  int group = -1;  // representative group
+  int group = -1;  // representative group (single-group kernels)
+  std::vector<int> variants;  // representative group of every variant (multi-group kernels), empty otherwise
   int nb_obs = 0;
   bool staged = true;  // bulk-copy staged stream (shared-memory prefetch) vs direct global loads
   int smem_bytes = 0;

@@ -8,6 +8,8 @@
 // they are compiled concurrently and each streams its own tile list (api.cu).
 #include <nvrtc.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -36,6 +38,72 @@ static std::string plane_name(uint32_t nb, uint32_t byte, uint32_t bit) {
   return os.str();
 }
 
+// struct <name> { T, NACC, NB, run() }: the XOR network of one group, masks baked in.
+static void emit_terms(std::ostringstream& os, const std::string& name, const qcut_group_desc& gd, const uint8_t* masks) {
+  const uint32_t T = gd.n_terms, nb = gd.nb_obs, nacc = (T + 3) / 4;
+  os << "// " << T << " terms on " << nb << "-byte rows\n";
+  os << "struct " << name << " {\n";
+  os << "  static const int T = " << T << ";\n  static const int NACC = " << nacc << ";\n";
+  os << "  static const int NB = " << nb << ";\n";
+  os << "  static QCUT_MDEV void run(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, "
+        "const uint32_t qp, uint32_t* __restrict__ acc) {\n";
+  os << "    (void)Q;\n";
+  for (uint32_t t = 0; t < T; ++t) {
+    const uint8_t* row = masks + gd.mask_offset + (size_t)t * nb;
+    // term t lives in field t / NACC of packed register t % NACC: consecutive terms touch different
+    // registers, so their popcount -> add chains are independent
+    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(qp";
+    for (uint32_t byte = 0; byte < nb; ++byte)
+      for (uint32_t bit = 0; bit < 8; ++bit)
+        if ((row[byte] >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
+    os << ")";
+    if (t / nacc) os << " << " << 8 * (t / nacc);
+    os << ";\n";
+  }
+  os << "  }\n};\n\n";
+}
+
+// One kernel for many small groups: every group becomes a __noinline__ device function (so that
+// compile time stays linear in the number of groups) and the kernel dispatches on the group's
+// variant index; the schedule lists a kernel's tiles variant by variant, so at any moment the SMs
+// execute a handful of functions.
+std::string generate_multi_source(const std::vector<const qcut_group_desc*>& gds, const uint8_t* masks, int threads) {
+  std::ostringstream os;
+  os << kPrelude << "\n";
+  for (size_t v = 0; v < gds.size(); ++v) {
+    emit_terms(os, "Terms" + std::to_string(v), *gds[v], masks);
+    os << "__device__ __noinline__ void qcut_variant_" << v
+       << "(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns, int lane,\n"
+          "                                    unsigned long long* __restrict__ tally) {\n"
+          "  uint32_t acc[Terms" << v << "::NACC];\n"
+          "  qcut_lane_tile<Terms" << v << "::NB, Terms" << v << ">(obs, qpd, nbq, ns, lane, acc);\n"
+          "  qcut_flush<Terms" << v << "::T>(acc, ns, lane, tally);\n"
+          "}\n\n";
+  }
+  os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 2)\n"
+        "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+        "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+        "                  unsigned long long* __restrict__ tallies, const QcutGroup* __restrict__ groups) {\n"
+        "  const int lane = threadIdx.x & 31;\n"
+        "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+        "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
+        "       tile += n_warps) {\n"
+        "    const QcutTile te = tiles[tile];\n"
+        "    const QcutPub pub = pubs[te.pub];\n"
+        "    const QcutGroup grp = groups[pub.group];\n"
+        "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+        "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+        "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+        "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * grp.nb_obs;\n"
+        "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+        "    unsigned long long* __restrict__ tally = tallies + pub.tally_offset;\n"
+        "    switch (grp.variant) {\n";
+  for (size_t v = 0; v < gds.size(); ++v)
+    os << "      case " << v << ": qcut_variant_" << v << "(obs, qpd, (int)pub.nb_qpd, ns, lane, tally); break;\n";
+  os << "      default: break;\n    }\n  }\n}\n";
+  return os.str();
+}
+
 // The translation unit for one group.  Pure host code.
 std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out,
                                    bool staged, int threads, int prefetch) {
@@ -48,27 +116,7 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
 
   std::ostringstream os;
   os << kPrelude << "\n";
-  os << "// " << T << " terms on " << nb << "-byte rows\n";
-  os << "struct Terms {\n";
-  os << "  static const int T = " << T << ";\n  static const int NACC = " << (T + 3) / 4 << ";\n";
-  os << "  static const int NB = " << nb << ";\n";
-  os << "  static QCUT_MDEV void run(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, "
-        "const uint32_t qp, uint32_t* __restrict__ acc) {\n";
-  os << "    (void)Q;\n";
-  for (uint32_t t = 0; t < T; ++t) {
-    const uint8_t* row = masks + gd.mask_offset + (size_t)t * nb;
-    // term t lives in field t / NACC of packed register t % NACC: consecutive terms touch different
-    // registers, so their popcount -> add chains are independent
-    const uint32_t nacc = (T + 3) / 4;
-    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(qp";
-    for (uint32_t byte = 0; byte < nb; ++byte)
-      for (uint32_t bit = 0; bit < 8; ++bit)
-        if ((row[byte] >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
-    os << ")";
-    if (t / nacc) os << " << " << 8 * (t / nacc);
-    os << ";\n";
-  }
-  os << "  }\n};\n\n";
+  emit_terms(os, "Terms", gd, masks);
   os << "#ifndef QCUT_HOST_EMU\n";
   os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n";
   if (staged) {
@@ -234,13 +282,23 @@ int compile_sliced_source(const std::string& source, std::vector<char>* cubin, s
 }
 
 // Generate + compile (concurrently) + load the kernels of plan->jit[*].group.
-int jit_build(qcut_plan* plan) {
+int jit_build(qcut_plan* plan, bool load) {
   const size_t n = plan->jit.size();
   if (n == 0) return QCUT_OK;
   std::vector<int> rcs(n, QCUT_OK);
   std::vector<std::string> errors(n);
   auto work = [&](size_t i) {
     JitKernel& jk = plan->jit[i];
+    if (!jk.variants.empty()) {
+      std::vector<const qcut_group_desc*> gds;
+      for (int g : jk.variants) gds.push_back(&plan->groups[g]);
+      jk.threads = 256;
+      jk.min_blocks = 2;
+      jk.staged = false;
+      jk.source = generate_multi_source(gds, plan->masks.data(), jk.threads);
+      rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
+      return;
+    }
     jk.staged = (plan->flags & QCUT_PLAN_STAGED) != 0;
     jk.nb_obs = (int)plan->groups[jk.group].nb_obs;
     // tuning knobs (experiments only): QCUT_JIT_THREADS (CTA size), QCUT_JIT_MINBLOCKS (launch bound)
@@ -254,15 +312,21 @@ int jit_build(qcut_plan* plan) {
     jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads, prefetch);
     rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
   };
+  std::atomic<size_t> next{0};
+  auto drain = [&]() {
+    for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) work(i);
+  };
+  const size_t n_threads = std::min<size_t>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
   std::vector<std::thread> pool;
-  for (size_t i = 1; i < n; ++i) pool.emplace_back(work, i);
-  work(0);
+  for (size_t t = 1; t < n_threads; ++t) pool.emplace_back(drain);
+  drain();
   for (auto& th : pool) th.join();
   for (size_t i = 0; i < n; ++i)
     if (rcs[i] != QCUT_OK) {
       set_error(errors[i]);
       return rcs[i];
     }
+  if (!load) return QCUT_OK;  // compile check only (no device needed)
   for (JitKernel& jk : plan->jit) {
     cudaError_t err = cudaLibraryLoadData(&jk.library, jk.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (err == cudaSuccess) err = cudaLibraryGetKernel(&jk.kernel, jk.library, "qcut_tally_sliced");
@@ -289,7 +353,8 @@ void jit_release(qcut_plan* plan) {
 }
 
 int launch_tally_jit(const JitKernel& jk, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
-                     const TileEntry* d_tiles, int64_t n_tiles, int64_t* d_tallies, cudaStream_t stream) {
+                     const TileEntry* d_tiles, int64_t n_tiles, int64_t* d_tallies, const GroupDev* d_groups,
+                     cudaStream_t stream) {
   if (n_tiles <= 0) return QCUT_OK;
   if (!jk.kernel) {
     set_error("qcut_tally_launch: specialised kernel was not loaded");
@@ -302,7 +367,7 @@ int launch_tally_jit(const JitKernel& jk, const uint8_t* d_data, const qcut_pub_
   const int64_t cap = (int64_t)sm_count() * jk.min_blocks;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   unsigned long long* tallies = reinterpret_cast<unsigned long long*>(d_tallies);
-  void* args[] = {(void*)&d_data, (void*)&d_pubs, (void*)&d_tiles, (void*)&n_tiles, (void*)&tallies};
+  void* args[] = {(void*)&d_data, (void*)&d_pubs, (void*)&d_tiles, (void*)&n_tiles, (void*)&tallies, (void*)&d_groups};
   QCUT_CUDA(cudaLaunchKernel(reinterpret_cast<const void*>(jk.kernel), dim3(grid), dim3(jk.threads), args,
                              (size_t)jk.smem_bytes, stream));
   return QCUT_OK;

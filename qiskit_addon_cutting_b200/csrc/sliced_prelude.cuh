@@ -51,6 +51,9 @@ struct QcutPub {
   uint64_t obs_offset, qpd_offset, tally_offset;
   uint32_t shots, group, nb_qpd, reserved;
 };
+struct QcutGroup {
+  uint32_t n_terms, nb_obs, n_words, word_offset, kernel, variant, reserved[2];
+};
 struct QcutTile {
   uint32_t pub;          // PUB that owns the tile
   uint32_t tile_in_pub;  // shots [tile_in_pub * QCUT_TILE_SHOTS, ...) of that PUB

@@ -34,7 +34,7 @@ UNIT = "shot-terms/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4_heavy_hex")
@@ -145,7 +145,7 @@ class ClockSampler:
         self.samples, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device_index)],
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(device_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -252,8 +252,13 @@ def ours_arm(args):
     k1_bytes = int((tables.pubs["shots"].astype(np.int64) * (nbo + nbq)).sum()) + 8 * tables.n_tallies
     peak, peak_src = peaks()
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    for path in sorted((ROOT / "profiles").glob("*_k1_traffic.json")):
+        rec = json.loads(path.read_text())
+        if rec.get("workload") == args.workload and abs(rec.get("scale", 1.0) - args.scale) < 1e-9:
+            traffic = rec["traffic_bytes_per_k1_launch"]  # dram read + write of one qcut_tally_launch (ncu --set full)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "K1 parity tally (all launches of qcut_tally_launch)",
+                "traffic": traffic, "kernel": "K1 parity tally (all launches of qcut_tally_launch)",
                 "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms, "peak_source": peak_src,
                 "k1_share_of_step": k1_ms / ms_per_step, "k2_plus_allreduce_ms": k2_ms}
 

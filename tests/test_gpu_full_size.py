@@ -1,0 +1,87 @@
+"""Parity at BASELINE-sized workloads (B200): data generated on the device, checked through properties that do
+not need the slow oracle on every byte:
+
+* the three K1 implementations (NVRTC-specialised, run-time-mask bit-sliced, generic AND/POPC) are independent
+  code paths and must produce identical int64 tallies on the same resident bytes;
+* a seeded subsample of PUBs is copied back and recomputed by the C oracle (bit-exact);
+* identity: a term with an empty mask tallies S - 2 * #(shots with odd qpd parity);
+* the full expectation values of two runs (two schedules, same data) are bit-identical (determinism).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import workloads as W
+from oracle import c_oracle
+from qiskit_addon_cutting_b200 import _lib, engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(tables, data, flags):
+    batch = engine.DeviceBatch(tables, data, flags=flags)
+    out = batch.run().clone()
+    torch.cuda.synchronize()
+    return batch, batch.tallies[: tables.n_tallies].clone(), out
+
+
+@pytest.mark.parametrize("name,scale", [("cfg4_heavy_hex", 0.1), ("cfg5_molecular", 0.15), ("cfg3_wide_dense", 0.3),
+                                        ("cfg3_wide_local", 1.0), ("cfg2_wire", 1.0), ("cfg1_tutorial", 1.0)])
+def test_three_kernels_agree_and_match_oracle_subsample(lib, name, scale):
+    w = W.get_workload(name, scale)
+    tables = W.build_tables(w)
+    data = W.device_data(tables, seed=w.seed)
+    b_jit, t_jit, out_jit = _run(tables, data, 0)
+    b_rt, t_rt, out_rt = _run(tables, data, _lib.PLAN_NO_JIT)
+    assert torch.equal(t_jit, t_rt), "specialised vs run-time-mask kernel"
+    assert max(b_jit.plan.kernels()) >= _lib.KERNEL_JIT0 and max(b_rt.plan.kernels()) <= _lib.KERNEL_SLICED_RT
+    if tables.work <= 3e10:  # the generic kernel is POPC bound: keep it to a few hundred ms
+        _, t_gen, out_gen = _run(tables, data, _lib.PLAN_GENERIC_ONLY)
+        assert torch.equal(t_jit, t_gen), "specialised vs generic kernel"
+        assert torch.equal(out_jit, out_gen)
+    assert torch.equal(out_jit, out_rt)
+    # determinism across runs
+    _, t_again, out_again = _run(tables, data, 0)
+    assert torch.equal(t_jit, t_again) and torch.equal(out_jit, out_again)
+
+    # seeded subsample of PUBs vs the C oracle
+    rng = np.random.default_rng(w.seed)
+    picks = rng.choice(len(tables.pubs), size=min(24, len(tables.pubs)), replace=False)
+    t_host = t_jit.cpu().numpy()
+    for p in picks:
+        pub = tables.pubs[p]
+        grp = tables.groups[pub["group"]]
+        nb, T, S, nbq = int(grp["nb_obs"]), int(grp["n_terms"]), int(pub["shots"]), int(pub["nb_qpd"])
+        S = min(S, 200_000)  # bound the CPU work for 10^6-shot PUBs: compare a prefix via a separate tally below
+        obs = data[int(pub["obs_offset"]): int(pub["obs_offset"]) + S * nb].cpu().numpy().reshape(S, nb)
+        qpd = data[int(pub["qpd_offset"]): int(pub["qpd_offset"]) + S * nbq].cpu().numpy().reshape(S, nbq)
+        masks = tables.masks[int(grp["mask_offset"]): int(grp["mask_offset"]) + T * nb].reshape(T, nb)
+        _, want = c_oracle.pub(obs, qpd, masks)
+        if S == int(pub["shots"]):
+            assert np.array_equal(t_host[int(pub["tally_offset"]): int(pub["tally_offset"]) + T], want), (name, int(p))
+        # identity / empty-mask terms: tally = S - 2 * #(odd qpd parity)
+        empty = np.flatnonzero(~masks.any(axis=1))
+        if empty.size and S == int(pub["shots"]):
+            odd = int((np.bitwise_count(qpd).sum(axis=1) & 1).sum())
+            assert t_host[int(pub["tally_offset"]) + int(empty[0])] == S - 2 * odd
+
+
+def test_prefix_tallies_of_million_shot_pubs(lib):
+    """cfg3 shape (10^6 shots per PUB): a PUB truncated to its first S' shots must tally like the oracle on that prefix."""
+    w = W.get_workload("cfg3_wide_dense", 0.06)  # 2 tuples x 2 subsystems
+    tables = W.build_tables(w)
+    data = W.device_data(tables, seed=7)
+    for shots in (4096 * 3 + 17, 150_001):
+        t2 = W.build_tables(w)
+        t2.pubs["shots"] = shots
+        _, tallies, _ = _run(t2, data, 0)
+        tallies = tallies.cpu().numpy()
+        pub = t2.pubs[1]
+        grp = t2.groups[pub["group"]]
+        nb, T = int(grp["nb_obs"]), int(grp["n_terms"])
+        obs = data[int(pub["obs_offset"]): int(pub["obs_offset"]) + shots * nb].cpu().numpy().reshape(shots, nb)
+        qpd = data[int(pub["qpd_offset"]): int(pub["qpd_offset"]) + shots].cpu().numpy().reshape(shots, 1)
+        masks = t2.masks[int(grp["mask_offset"]): int(grp["mask_offset"]) + T * nb].reshape(T, nb)
+        _, want = c_oracle.pub(obs, qpd, masks)
+        assert np.array_equal(tallies[int(pub["tally_offset"]): int(pub["tally_offset"]) + T], want)

@@ -214,8 +214,9 @@ reduce_partial_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* _
 // consecutive tuples and every lane keeps its running sum in a register (ascending i inside the
 // chunk).  No shared memory; the descriptor -> tally load chains of B tuples x L subsystems are in
 // flight together per lane and up to 64 warps per SM hide the rest of the latency.
-constexpr int kStreamChunk = 256;
 constexpr int kStreamWarps = 4;
+constexpr int kStreamSub = 64;                              // tuples per warp
+constexpr int kStreamChunk = kStreamWarps * kStreamSub;    // tuples per CTA = one partial sum
 
 template <typename TallyT, int L>
 __global__ void __launch_bounds__(kStreamWarps * 32)
@@ -225,31 +226,65 @@ reduce_stream_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* __
                      const double* __restrict__ coeffs, int64_t n_coeffs, int n_obs, int64_t n_chunks,
                      double* __restrict__ partial) {
   constexpr int B = (L <= 2) ? 8 : 4;
+  __shared__ double s_sub[kStreamWarps][32];
   const int lane = threadIdx.x & 31;
-  const int64_t chunk = (int64_t)blockIdx.y * kStreamWarps + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int64_t chunk = blockIdx.y;
   const int k = blockIdx.x * 32 + lane;
-  if (chunk >= n_chunks || k >= n_obs) return;
-  const int64_t i0 = chunk * kStreamChunk;
-  const int n_i = (int)min((int64_t)kStreamChunk, n_coeffs - i0);
+  const int64_t i0 = chunk * kStreamChunk + (int64_t)warp * kStreamSub;
+  const int n_i = (int)max((int64_t)0, min((int64_t)kStreamSub, n_coeffs - i0));
   double sum = 0.0;
-  if constexpr (L > 0) {
-    SlotRef slots[L];
-    load_slots<L>(labels, lookup_start, lookup, k, slots);
-    for (int base = 0; base < n_i; base += B) {
-      int64_t idx[B];
-      double term[B];
+  if (k < n_obs && n_i > 0) {
+    if constexpr (L > 0) {
+      SlotRef slots[L];
+      load_slots<L>(labels, lookup_start, lookup, k, slots);
+      for (int base = 0; base < n_i; base += B) {
+        int64_t idx[B];
+        double term[B];
 #pragma unroll
-      for (int j = 0; j < B; ++j) idx[j] = i0 + min(base + j, n_i - 1);  // clamped: always a valid tuple
-      batch_terms<TallyT, L, B>(tallies, pubs, slots, coeffs, idx, term);
+        for (int j = 0; j < B; ++j) idx[j] = i0 + min(base + j, n_i - 1);  // clamped: always a valid tuple
+        batch_terms<TallyT, L, B>(tallies, pubs, slots, coeffs, idx, term);
 #pragma unroll
-      for (int j = 0; j < B; ++j)
-        if (base + j < n_i) sum = __dadd_rn(sum, term[j]);  // ascending i
+        for (int j = 0; j < B; ++j)
+          if (base + j < n_i) sum = __dadd_rn(sum, term[j]);  // ascending i
+      }
+    } else {
+      for (int ii = 0; ii < n_i; ++ii)
+        sum = __dadd_rn(sum, general_term<TallyT>(tallies, pubs, labels, n_labels, lookup_start, lookup, coeffs, i0 + ii, k));
     }
-  } else {
-    for (int ii = 0; ii < n_i; ++ii)
-      sum = __dadd_rn(sum, general_term<TallyT>(tallies, pubs, labels, n_labels, lookup_start, lookup, coeffs, i0 + ii, k));
   }
-  partial[chunk * n_obs + k] = sum;
+  s_sub[warp][lane] = sum;
+  __syncthreads();
+  if (warp == 0 && k < n_obs) {
+    double total = s_sub[0][lane];
+#pragma unroll
+    for (int w = 1; w < kStreamWarps; ++w) total = __dadd_rn(total, s_sub[w][lane]);  // ascending sub-chunk order
+    partial[chunk * n_obs + k] = total;
+  }
+}
+
+// Second level for large problems: segment s sums kCombineSeg consecutive chunk partials in ascending
+// order (thread <-> (segment, observable)); reduce_combine_kernel then sums the segments.
+constexpr int kCombineSeg = 32;
+
+__global__ void __launch_bounds__(128)
+reduce_segment_kernel(const double* __restrict__ partial, int64_t n_chunks, int n_obs, double* __restrict__ seg_out) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  if (k >= n_obs) return;
+  const int64_t c_begin = (int64_t)blockIdx.y * kCombineSeg;
+  double sum = 0.0;
+  for (int64_t c0 = c_begin; c0 < c_begin + kCombineSeg && c0 < n_chunks; c0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t c = c0 + j;
+      v[j] = __ldg(partial + (c < n_chunks ? c : n_chunks - 1) * n_obs + k);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < n_chunks) sum = __dadd_rn(sum, v[j]);
+  }
+  seg_out[(int64_t)blockIdx.y * n_obs + k] = sum;
 }
 
 __global__ void __launch_bounds__(128)
@@ -296,7 +331,7 @@ static int launch_level(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, co
     reduce_partial_kernel<TallyT, kReduceChunk, L><<<grid, kReduceThreads, smem, stream>>>(
         d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, partial);
   } else {
-    const dim3 grid((n_obs + 31) / 32, (unsigned)((chunks + kStreamWarps - 1) / kStreamWarps));
+    const dim3 grid((n_obs + 31) / 32, (unsigned)chunks);
     reduce_stream_kernel<TallyT, L><<<grid, kStreamWarps * 32, 0, stream>>>(
         d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, chunks, partial);
   }
@@ -313,7 +348,7 @@ int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qc
                   void* d_workspace, bool single_slot, cudaStream_t stream) {
   if (n_obs <= 0) return QCUT_OK;
   const int64_t chunks = num_chunks(n_coeffs);
-  if (chunks > 65535 * (int64_t)kStreamWarps) {
+  if (chunks > 65535) {
     set_error("qcut_reduce_launch: too many coefficients per rank");
     return QCUT_ERR_INVALID;
   }
@@ -332,7 +367,15 @@ int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qc
   }
 #undef QCUT_LEVEL
   if (rc != QCUT_OK) return rc;
-  reduce_combine_kernel<<<(n_obs + 127) / 128, 128, 0, stream>>>(partial, chunks, n_obs, d_out);
+  if (chunks > kCombineSeg) {
+    const int64_t segs = (chunks + kCombineSeg - 1) / kCombineSeg;
+    double* seg_out = partial + chunks * (int64_t)n_obs;
+    reduce_segment_kernel<<<dim3((n_obs + 127) / 128, (unsigned)segs), 128, 0, stream>>>(partial, chunks, n_obs, seg_out);
+    QCUT_CUDA(cudaGetLastError());
+    reduce_combine_kernel<<<(n_obs + 127) / 128, 128, 0, stream>>>(seg_out, segs, n_obs, d_out);
+  } else {
+    reduce_combine_kernel<<<(n_obs + 127) / 128, 128, 0, stream>>>(partial, chunks, n_obs, d_out);
+  }
   QCUT_CUDA(cudaGetLastError());
   return QCUT_OK;
 }
@@ -345,7 +388,9 @@ template int launch_reduce<double>(const double*, const qcut_pub_desc*, const qc
                                    double*, void*, bool, cudaStream_t);
 
 size_t reduce_workspace_bytes(int64_t n_coeffs, int n_obs) {
-  return (size_t)num_chunks(n_coeffs) * (size_t)(n_obs > 0 ? n_obs : 1) * sizeof(double);
+  const size_t chunks = (size_t)num_chunks(n_coeffs);
+  const size_t segs = (chunks + kCombineSeg - 1) / kCombineSeg;
+  return (chunks + segs) * (size_t)(n_obs > 0 ? n_obs : 1) * sizeof(double);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -138,6 +138,19 @@ typedef QcutSrcGlobal QcutSrcShared;  // the harness copies the step's bytes int
 template <int S>
 QCUT_DEV uint32_t qcut_shr(uint32_t x) { return __umulhi(x, 1u << (32 - S)); }
 
+// Bit select (x & M) | (y & ~M) as ONE LOP3 (lut 0xE4) with M as the instruction's single immediate.
+// Written in C, nvcc folds M and ~M into two immediates and emits two LOP3 per select.
+template <uint32_t M>
+QCUT_DEV uint32_t qcut_sel(uint32_t x, uint32_t y) {
+#ifndef QCUT_HOST_EMU
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(x), "r"(y), "n"(M));
+  return d;
+#else
+  return (x & M) | (y & ~M);
+#endif
+}
+
 // In-register 32x32 bit-matrix transposition: afterwards bit r of a[i] is bit i of the old a[r].
 // Two byte-granular stages are single PRMTs; the three bit-granular stages are one LOP3 select per
 // output word with both shifts on the FMA pipe (IMAD.SHL / IMAD.HI).
@@ -159,22 +172,22 @@ QCUT_DEV void qcut_transpose32(uint32_t* a) {
   for (int j = 0; j < 32; ++j) {
     if (j & 4) continue;
     const uint32_t x = a[j], y = a[j + 4];
-    a[j] = (x & 0x0F0F0F0Fu) | ((y << 4) & 0xF0F0F0F0u);
-    a[j + 4] = (qcut_shr<4>(x) & 0x0F0F0F0Fu) | (y & 0xF0F0F0F0u);
+    a[j] = qcut_sel<0x0F0F0F0Fu>(x, y << 4);
+    a[j + 4] = qcut_sel<0x0F0F0F0Fu>(qcut_shr<4>(x), y);
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j & 2) continue;
     const uint32_t x = a[j], y = a[j + 2];
-    a[j] = (x & 0x33333333u) | ((y << 2) & 0xCCCCCCCCu);
-    a[j + 2] = (qcut_shr<2>(x) & 0x33333333u) | (y & 0xCCCCCCCCu);
+    a[j] = qcut_sel<0x33333333u>(x, y << 2);
+    a[j + 2] = qcut_sel<0x33333333u>(qcut_shr<2>(x), y);
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     if (j & 1) continue;
     const uint32_t x = a[j], y = a[j + 1];
-    a[j] = (x & 0x55555555u) | ((y << 1) & 0xAAAAAAAAu);
-    a[j + 1] = (qcut_shr<1>(x) & 0x55555555u) | (y & 0xAAAAAAAAu);
+    a[j] = qcut_sel<0x55555555u>(x, y << 1);
+    a[j + 1] = qcut_sel<0x55555555u>(qcut_shr<1>(x), y);
   }
 }
 

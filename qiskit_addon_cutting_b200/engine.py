@@ -286,7 +286,10 @@ class DeviceBatch:
             ),
             "qcut_reduce_launch",
         )
-        return 2 if t.n_obs > 0 else 0
+        if t.n_obs <= 0:
+            return 0
+        n_chunks = 1 if len(t.coeffs) <= 1024 else -(-len(t.coeffs) // 256)
+        return 3 if n_chunks > 32 else 2
 
     def run(self) -> torch.Tensor:
         self.launch_tally()

@@ -39,24 +39,65 @@ static std::string plane_name(uint32_t nb, uint32_t byte, uint32_t bit) {
 }
 
 // struct <name> { T, NACC, NB, run() }: the XOR network of one group, masks baked in.
+// Terms are evaluated along a greedy nearest-neighbour chain in Hamming distance: the parity word of a
+// term is either built from scratch (qp ^ its planes) or from the previous term's word XOR the planes
+// in which the two masks differ, whichever needs fewer LOP3 -- dense or structured mask sets (long
+// shared Z strings) share most of their work this way, at the cost of one live register.
 static void emit_terms(std::ostringstream& os, const std::string& name, const qcut_group_desc& gd, const uint8_t* masks) {
   const uint32_t T = gd.n_terms, nb = gd.nb_obs, nacc = (T + 3) / 4;
+  auto row = [&](uint32_t t) { return masks + gd.mask_offset + (size_t)t * nb; };
+  auto weight = [&](uint32_t t) {
+    int w = 0;
+    for (uint32_t b = 0; b < nb; ++b) w += __builtin_popcount(row(t)[b]);
+    return w;
+  };
+  auto dist = [&](uint32_t s, uint32_t t) {
+    int d = 0;
+    for (uint32_t b = 0; b < nb; ++b) d += __builtin_popcount((unsigned)(row(s)[b] ^ row(t)[b]));
+    return d;
+  };
+  // evaluation order
+  std::vector<uint32_t> order;
+  std::vector<bool> incremental(T, false);
+  std::vector<bool> done(T, false);
+  uint32_t prev = 0;
+  for (uint32_t step = 0; step < T; ++step) {
+    uint32_t best = T;
+    int best_cost = 1 << 30;
+    bool best_inc = false;
+    for (uint32_t t = 0; t < T; ++t) {
+      if (done[t]) continue;
+      const int direct = weight(t);                            // planes XORed onto qp
+      const int inc = step ? dist(prev, t) : (1 << 29);        // planes XORed onto the previous word
+      const int cost = std::min(direct, inc);
+      if (cost < best_cost) { best_cost = cost; best = t; best_inc = inc < direct; }
+    }
+    done[best] = true;
+    incremental[best] = best_inc;
+    order.push_back(best);
+    prev = best;
+  }
   os << "// " << T << " terms on " << nb << "-byte rows\n";
   os << "struct " << name << " {\n";
   os << "  static const int T = " << T << ";\n  static const int NACC = " << nacc << ";\n";
   os << "  static const int NB = " << nb << ";\n";
   os << "  static QCUT_MDEV void run(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, "
         "const uint32_t qp, uint32_t* __restrict__ acc) {\n";
-  os << "    (void)Q;\n";
-  for (uint32_t t = 0; t < T; ++t) {
-    const uint8_t* row = masks + gd.mask_offset + (size_t)t * nb;
+  os << "    (void)Q;\n    uint32_t x;\n";
+  for (uint32_t i = 0; i < T; ++i) {
+    const uint32_t t = order[i];
+    const uint8_t* cur = row(t);
+    const uint8_t* old = i ? row(order[i - 1]) : cur;
+    os << "    x = " << (incremental[t] ? "x" : "qp");
+    for (uint32_t byte = 0; byte < nb; ++byte)
+      for (uint32_t bit = 0; bit < 8; ++bit) {
+        const unsigned sel = incremental[t] ? (unsigned)(cur[byte] ^ old[byte]) : (unsigned)cur[byte];
+        if ((sel >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
+      }
+    os << ";\n";
     // term t lives in field t / NACC of packed register t % NACC: consecutive terms touch different
     // registers, so their popcount -> add chains are independent
-    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(qp";
-    for (uint32_t byte = 0; byte < nb; ++byte)
-      for (uint32_t bit = 0; bit < 8; ++bit)
-        if ((row[byte] >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
-    os << ")";
+    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(x)";
     if (t / nacc) os << " << " << 8 * (t / nacc);
     os << ";\n";
   }

@@ -10,13 +10,14 @@ from __future__ import annotations
 import ctypes as C
 import hashlib
 import subprocess
+import tempfile
 from pathlib import Path
 
 import numpy as np
 
 from qiskit_addon_cutting_b200 import _lib
 
-BUILD = Path(__file__).resolve().parent / "_emu_build"
+BUILD = Path(tempfile.gettempdir()) / "qcut_b200_emu_build"  # outside the repo: built artefacts do not travel
 
 SHIM = r"""
 #include <cstdint>

@@ -193,8 +193,19 @@ def ours_arm(args):
         entry.build_library()
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier()
+        # NCCL announces its version on stdout at communicator creation; the contract is ONE JSON line on
+        # stdout, so stdout is pointed at stderr until the first collective has run.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     w = W.get_workload(args.workload, args.scale)
     tables = W.build_tables(w, rank, world)

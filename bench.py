@@ -277,7 +277,7 @@ def ours_arm(args):
     e2e = None
     if not args.no_e2e:
         host = np.empty(tables.data_bytes, dtype=np.uint8)
-        torch.from_numpy(host).copy_(data)
+        torch.from_numpy(host).copy_(data[: tables.data_bytes])
         results = W.host_results(w, tables, host)
         coeffs_all = w.coefficients(rank, world)
         lo = rank * w.n_coeffs
@@ -315,7 +315,25 @@ def ours_arm(args):
             return o, q
 
         wk, secs = run_reference_port(tables, sample, fetch)
-        cpu = {"value": wk / secs, "unit": UNIT, "cores": 1, "kind": "port",
+        compiled = None
+        try:  # extra data point: the C restatement of the same loop (sequential fp64 included), all host threads
+            from oracle import c_oracle
+
+            n_sub = min(len(tables.pubs), 256)
+            sub = tables.pubs[:n_sub].copy()
+            hi = int(sub["qpd_offset"][-1]) + int(sub["shots"][-1]) * int(sub["nb_qpd"][-1]) + 16
+            sub_bytes = data[:hi].cpu().numpy()
+            sub["tally_offset"] -= sub["tally_offset"][0]
+            n_t = int((tables.groups["n_terms"][sub["group"]]).sum())
+            t0 = time.perf_counter()
+            c_oracle.pubs(sub_bytes, sub, tables.groups, tables.masks, n_t, want_seq=True, n_threads=0)
+            dt = time.perf_counter() - t0
+            compiled = {"value": float((sub["shots"].astype(np.int64) * tables.groups["n_terms"][sub["group"]]).sum()) / dt,
+                        "unit": UNIT, "cores": c_oracle.max_threads(), "kind": "port (oracle_seq.c, pthreads over PUBs)",
+                        "sample": f"first {n_sub} PUBs of the resident data"}
+        except Exception as exc:  # the C oracle is optional test infrastructure
+            compiled = {"unavailable": repr(exc)}
+        cpu = {"value": wk / secs, "unit": UNIT, "cores": 1, "kind": "port", "compiled_port": compiled,
                "sample": f"{len(sample)} PUBs x ~{sample[0][1]} shots of the same resident data "
                          f"({secs:.1f} s of the python port of the reference loop; the reference is single-threaded)"}
 

@@ -20,7 +20,8 @@
  *     byte matrices, observable_measurements (shots x nb_obs) and qpd_measurements
  *     (shots x nb_qpd), exactly the bytes of Qiskit's BitArray.array: big-endian within a
  *     row (reference cutting_reconstruction.py:152-158).  Matrices start at 16-byte aligned
- *     offsets and the buffer is readable up to the next multiple of 16 after each matrix.
+ *     offsets; the buffer must be readable QCUT_DATA_SLACK bytes past the end of the last matrix
+ *     (kernels load whole 16-byte chunks / 16-shot groups and mask what lies past a PUB's end).
  *   - masks: per group, n_terms x nb_obs bytes, big-endian rows (same memory order as the
  *     shot rows, so kernels AND raw bytes; reference utils/observable_grouping.py:140-151).
  *   - tallies: int64, tally[pub.tally_offset + t] = sum over shots of
@@ -42,6 +43,8 @@ extern "C" {
 #define QCUT_TILE_SHOTS 4096
 /* Widest observable row (bytes) the kernels accept: 64 bytes = 512 measured qubits per group. */
 #define QCUT_MAX_OBS_BYTES 64
+/* Readable slack required after the last byte of shot data (see the data layout note above). */
+#define QCUT_DATA_SLACK 128
 
 typedef enum qcut_status {
   QCUT_OK = 0,

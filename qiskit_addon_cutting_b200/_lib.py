@@ -19,6 +19,7 @@ LIB_PATH = PACKAGE_DIR / "libqcut_b200.so"
 
 TILE_SHOTS = 4096
 MAX_OBS_BYTES = 64
+DATA_SLACK = 128  # readable bytes required after the last matrix (QCUT_DATA_SLACK)
 ABI_VERSION = 3
 PLAN_NO_JIT = 1
 PLAN_GENERIC_ONLY = 2

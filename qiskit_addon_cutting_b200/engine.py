@@ -445,7 +445,7 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
     _lib.require_device()
     tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs)
     total = tables.data_bytes
-    data = torch.empty(total, dtype=torch.uint8, device="cuda")
+    data = torch.empty(total + _lib.DATA_SLACK, dtype=torch.uint8, device="cuda")
     if len(arrays):
         pinned = _pinned_buffer(_STAGING_BYTES)
         check(

@@ -33,6 +33,7 @@ def test_abi_version_and_structs(lib):
     header = (ROOT / "include" / "qcut_b200.h").read_text()
     assert f"#define QCUT_TILE_SHOTS {_lib.TILE_SHOTS}" in header
     assert f"#define QCUT_MAX_OBS_BYTES {_lib.MAX_OBS_BYTES}" in header
+    assert f"#define QCUT_DATA_SLACK {_lib.DATA_SLACK}" in header
     assert _lib.PUB_DTYPE.itemsize == 40 and _lib.GROUP_DTYPE.itemsize == 16
 
 

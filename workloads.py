@@ -260,7 +260,7 @@ def device_data(tables, seed: int):
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
-    n = tables.data_bytes
+    n = tables.data_bytes + 128  # QCUT_DATA_SLACK: readable slack after the last matrix
     words = (n + 7) // 8
     data = torch.randint(-(2**63), 2**63 - 1, (words,), dtype=torch.int64, device="cuda", generator=gen)
     return data.view(torch.uint8)[:n]

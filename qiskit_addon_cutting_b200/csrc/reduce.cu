@@ -320,7 +320,10 @@ static int launch_level(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, co
                         const double* d_coeffs, int64_t n_coeffs, int n_obs, double* partial, int64_t chunks,
                         cudaStream_t stream) {
   if (chunk_size(n_coeffs) == kReduceChunk) {
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    int dev__ = 0;
+    QCUT_CUDA(cudaGetDevice(&dev__));
+    bool& configured = configured_dev[dev__ & 63];  // the attribute is per device
     const size_t smem = sizeof(double) * kReduceObs * (kReduceChunk + 10);
     if (!configured) {
       QCUT_CUDA(cudaFuncSetAttribute(reduce_partial_kernel<TallyT, kReduceChunk, L>,

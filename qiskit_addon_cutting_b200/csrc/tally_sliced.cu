@@ -98,7 +98,10 @@ bool sliced_rt_supports(uint32_t nb_obs) { return nb_obs >= 1 && nb_obs <= 8; }
 int launch_tally_sliced_rt(const qcut_plan* plan, const uint8_t* d_data, const qcut_pub_desc* d_pubs,
                            const TileEntry* d_tiles, int64_t n_tiles, int64_t* d_tallies, cudaStream_t stream) {
   if (n_tiles <= 0) return QCUT_OK;
-  static bool configured = false;
+  static bool configured_dev[64] = {};
+  int dev__ = 0;
+  QCUT_CUDA(cudaGetDevice(&dev__));
+  bool& configured = configured_dev[dev__ & 63];  // the attribute is per device
   const size_t smem = (size_t)kRtWarps * kRtPlaneWords * sizeof(uint32_t);  // 64 KB per CTA
   if (!configured) {
     QCUT_CUDA(cudaFuncSetAttribute(tally_sliced_rt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -85,3 +85,47 @@ def test_prefix_tallies_of_million_shot_pubs(lib):
         masks = t2.masks[int(grp["mask_offset"]): int(grp["mask_offset"]) + T * nb].reshape(T, nb)
         _, want = c_oracle.pub(obs, qpd, masks)
         assert np.array_equal(tallies[int(pub["tally_offset"]): int(pub["tally_offset"]) + T], want)
+
+
+@pytest.mark.parametrize("shots,exact", [(1 << 20, True), (1_000_000, False)])
+def test_expectation_values_at_a_million_shots_vs_literal_oracle(lib, shots, exact):
+    """cfg3 shot count through the whole path (K1 + K2) against the C restatement of the reference's arithmetic
+    (sequential fp64 accumulation of +-fl(1/S) per shot, cutting_reconstruction.py:159).
+
+    S = 2^20: 1/S and every partial sum are exact, so the reference has no rounding noise and our result must be
+    bit-identical to it.  S = 10^6: the reference's own accumulation deviates from tally/S by up to ~6e-12 per
+    expectation value; we require |ours - reference arithmetic| <= 2e-11 * kappa and
+    |ours - exact| <= 4 ulp * kappa.
+    """
+    w = W.get_workload("cfg3_wide_dense", 0.06)  # 2 coefficient tuples x 2 subsystems x 100 terms
+    w.shots = shots
+    tables = W.build_tables(w)
+    data = W.device_data(tables, seed=11)
+    batch, tallies, out = _run(tables, data, 0)
+    host = data[: tables.data_bytes].cpu().numpy()
+    e_seq, tally = c_oracle.pubs(host, tables.pubs, tables.groups, tables.masks, tables.n_tallies, want_seq=True, n_threads=0)
+    assert np.array_equal(tallies.cpu().numpy(), tally)
+
+    def reduce(E):  # reference order: product over subsystems, sum over tuples (cutting_reconstruction.py:134-168)
+        res = np.zeros(tables.n_obs)
+        for i, c in enumerate(tables.coeffs):
+            cur = np.ones(tables.n_obs)
+            for lab in tables.labels:
+                for k in range(tables.n_obs):
+                    e0 = int(tables.lookup_start[int(lab["lookup_base"]) + k])
+                    slot = tables.lookup[e0]
+                    pub = tables.pubs[int(lab["pub_base"]) + i * int(lab["num_groups"]) + int(slot["group"])]
+                    cur[k] *= E[int(pub["tally_offset"]) + int(slot["term"])]
+            res += c * cur
+        return res
+
+    ours = out.cpu().numpy()
+    kappa = float(np.abs(tables.coeffs).sum())
+    exact_vals = reduce(tally / float(shots))
+    literal_vals = reduce(e_seq)
+    assert np.max(np.abs(ours - exact_vals)) <= 4 * np.finfo(np.float64).eps * kappa
+    assert [v.hex() for v in ours] == [v.hex() for v in exact_vals]
+    if exact:
+        assert [v.hex() for v in ours] == [v.hex() for v in literal_vals]
+    else:
+        assert np.max(np.abs(ours - literal_vals)) <= 2e-11 * kappa

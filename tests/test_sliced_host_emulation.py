@@ -81,3 +81,38 @@ def test_unsupported_widths_are_not_specialised(lib):
     assert _lib.generate_source(groups, masks, 0) == ""
     assert "struct Terms" in _lib.generate_source(groups, masks, 1)
     assert _lib.generate_source(groups, masks, 2) == ""
+
+
+def _guarded_copy(data: np.ndarray, used: int):
+    """Copy `data[:used + DATA_SLACK]` so that it ENDS at an inaccessible guard page: any emulated load past the
+    slack the C ABI promises (QCUT_DATA_SLACK) faults instead of silently reading a neighbour."""
+    import ctypes
+    import mmap
+
+    page = mmap.PAGESIZE
+    span = used + _lib.DATA_SLACK
+    total = (span + page - 1) // page * page + page
+    mm = mmap.mmap(-1, total, flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS, prot=mmap.PROT_READ | mmap.PROT_WRITE)
+    base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+    start = total - page - span
+    start -= start % 16  # keep the 16-byte alignment of the staged layout
+    view = np.frombuffer(mm, dtype=np.uint8)
+    view[start:start + used] = data[:used]
+    view[start + used: total - page] = 0x5A
+    libc = ctypes.CDLL(None)
+    assert libc.mprotect(ctypes.c_void_p(base + total - page), ctypes.c_size_t(page), 0) == 0  # PROT_NONE
+    return mm, view[start:]
+
+
+@pytest.mark.parametrize("nbits,qbits,shots", [(20, 1, 5), (53, 3, 77), (35, 9, 1030), (64, 1, 4097), (13, 1, 2049), (5, 2, 4100)])
+def test_emulated_loads_stay_inside_the_promised_slack(lib, nbits, qbits, shots):
+    rng = np.random.default_rng(nbits + shots)
+    observables = {"A": _cases.random_paulis(rng, 5, nbits, 1, nbits, "Z")}
+    coefficients = [(1.0, WeightType.EXACT)]
+    results = _cases.make_results(observables, 1, shots, qbits, seed=3)
+    tables, data, want = _stage_host(results, coefficients, observables)
+    mm, guarded = _guarded_copy(data, tables.data_bytes)
+    for engine_kind in ("jit", "rt"):
+        got, covered = _host_emu.emulate_tallies(tables, guarded, engine_kind)
+        assert covered.all() and np.array_equal(got, want)
+    del guarded

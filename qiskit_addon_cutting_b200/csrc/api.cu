@@ -73,7 +73,7 @@ static void assign_jit_kernels(qcut_plan* plan) {
     std::map<std::string, std::vector<int>> by_masks;
     for (int g = 0; g < n_groups; ++g) {
       const qcut_group_desc& gd = h_groups[g];
-      if (gd.n_terms < kJitMinTerms || !jit_supports(gd)) continue;
+      if (!jit_supports(gd) || (gd.n_terms < kJitMinTerms && gd.nb_obs <= 8)) continue;
       std::string key(reinterpret_cast<const char*>(&gd.nb_obs), sizeof(gd.nb_obs));
       key.append(reinterpret_cast<const char*>(h_masks + gd.mask_offset), (size_t)gd.n_terms * gd.nb_obs);
       by_masks[key].push_back(g);
@@ -100,7 +100,7 @@ static void assign_jit_kernels(qcut_plan* plan) {
     std::vector<const std::vector<int>*> small_sets;
     for (int g = 0; g < n_groups; ++g) {
       const qcut_group_desc& gd = h_groups[g];
-      if (taken[(size_t)g] || !jit_supports(gd)) continue;
+      if (taken[(size_t)g] || !jit_supports(gd) || gd.nb_obs > 8) continue;  // wide rows: per-group kernels only
       std::string key(reinterpret_cast<const char*>(&gd.nb_obs), sizeof(gd.nb_obs));
       key.append(reinterpret_cast<const char*>(h_masks + gd.mask_offset), (size_t)gd.n_terms * gd.nb_obs);
       auto ins = small.emplace(std::move(key), std::vector<int>());

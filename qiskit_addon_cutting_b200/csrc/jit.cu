@@ -27,12 +27,16 @@ constexpr uint32_t kMaxJitTerms = 384;  // packed 8-bit counters: ceil(T/4) regi
 
 bool jit_supports(const qcut_group_desc& gd) {
   const uint32_t nb = gd.nb_obs;
-  return nb >= 1 && nb <= 8 && gd.n_terms > 0 && gd.n_terms <= kMaxJitTerms;
+  return nb >= 1 && nb <= 16 && gd.n_terms > 0 && gd.n_terms <= kMaxJitTerms;
 }
 
 // Name of the register holding plane (byte B, bit b) for NB-byte rows (see sliced_prelude.cuh).
 static std::string plane_name(uint32_t nb, uint32_t byte, uint32_t bit) {
   std::ostringstream os;
+  if (nb > 8) {  // wide rows: planes parked in shared memory, P = &planes[0][lane]
+    os << "P[" << (8 * byte + bit) * 32 << "]";
+    return os.str();
+  }
   if (byte >= 4) os << "Q[" << 8 * (byte - 4) + bit << "]";
   else os << "P[" << 8 * (byte % 4) + bit << "]";
   return os.str();
@@ -158,6 +162,45 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   std::ostringstream os;
   os << kPrelude << "\n";
   emit_terms(os, "Terms", gd, masks);
+  if (nb > 8) {
+    // Wide rows: 4 warps per CTA, per-warp raw + plane buffers in dynamic shared memory.
+    os << "#ifndef QCUT_HOST_EMU\n"
+          "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
+          "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  extern __shared__ __align__(16) uint32_t qcut_smem[];\n"
+          "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n"
+          "  uint32_t* raw = qcut_smem + (size_t)warp * QcutWide<Terms::NB>::WARP_WORDS;\n"
+          "  uint32_t* planes = raw + QcutWide<Terms::NB>::RAW_WORDS;\n"
+          "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+          "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; tile < n_tiles; tile += n_warps) {\n"
+          "    const QcutTile te = tiles[tile];\n"
+          "    const QcutPub pub = pubs[te.pub];\n"
+          "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+          "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+          "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
+          "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "    uint32_t acc[Terms::NACC];\n"
+          "    qcut_lane_tile_wide<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc, raw, planes);\n"
+          "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
+          "  }\n"
+          "}\n"
+          "#else\n"
+          "extern \"C\" int qcut_emu_lane_tile(const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
+          "                                  uint32_t* odd_out) {\n"
+          "  static uint32_t raw[QcutWide<Terms::NB>::RAW_WORDS], planes[QcutWide<Terms::NB>::PLANE_WORDS];\n"
+          "  uint32_t acc[Terms::NACC];\n"
+          "  qcut_lane_tile_wide<Terms::NB, Terms>(obs, qpd, nbq, ns, lane, acc, raw, planes);\n"
+          "  for (int t = 0; t < Terms::T; ++t) odd_out[t] = (acc[t % Terms::NACC] >> (8 * (t / Terms::NACC))) & 0xFFu;\n"
+          "  return Terms::T;\n"
+          "}\n"
+          "extern \"C\" int qcut_emu_rt_lane_tile(int, const uint8_t*, const uint8_t*, int, int, int, const uint32_t*, int, int,\n"
+          "                                     uint32_t*) { return -1; }\n"
+          "#endif\n";
+    return os.str();
+  }
   os << "#ifndef QCUT_HOST_EMU\n";
   os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n";
   if (staged) {
@@ -372,7 +415,16 @@ int jit_build(qcut_plan* plan, bool load) {
     cudaError_t err = cudaLibraryLoadData(&jk.library, jk.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (err == cudaSuccess) err = cudaLibraryGetKernel(&jk.kernel, jk.library, "qcut_tally_sliced");
     if (err != cudaSuccess) return cuda_fail(err, "cudaLibraryLoadData(qcut_tally_sliced)");
-    if (jk.staged) {
+    if (jk.variants.empty() && jk.nb_obs > 8) {
+      // wide rows: 4 warps per CTA, per warp raw buffer (32 lanes x (4 NB + 1) words) + row / plane store
+      const int blocks = (jk.nb_obs + 3) / 4;
+      jk.threads = 128;
+      jk.min_blocks = 2;
+      jk.smem_bytes = 4 * (32 * (4 * jk.nb_obs + 1) + blocks * 32 * 32) * 4;
+      int dev = 0;
+      QCUT_CUDA(cudaGetDevice(&dev));
+      QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));
+    } else if (jk.staged) {
       // per warp: one step of observable rows + one step of qpd bytes, plus one mbarrier
       const int step_shots = jk.nb_obs == 1 ? 4096 : jk.nb_obs == 2 ? 2048 : 1024;
       const int stage = step_shots * (jk.nb_obs + 1);

@@ -442,6 +442,126 @@ QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __r
   }
 }
 
+// ---- wide rows (9..16 bytes): rows staged through shared memory, bit-planes parked in shared memory ----
+// Up to 128 bit-planes do not fit the register file, so the blocks are transposed one at a time and the
+// planes are parked in shared memory ([plane][lane], conflict free); the generated term code then reads
+// planes at *static* shared-memory offsets (`P[p * 32]`).  Rows are cut out of a per-warp raw buffer that
+// the warp fills with coalesced 128-bit loads: lane l owns 16 consecutive shots per group (16 * NB
+// contiguous bytes), stored at a stride of 4 * NB + 1 words so that the lanes' row reads hit 32 banks.
+template <int NB>
+struct QcutWide {
+  static const int BLOCKS = (NB + 3) / 4;
+  static const int RAW_STRIDE = 4 * NB + 1;                 // words per lane
+  static const int RAW_WORDS = 32 * RAW_STRIDE;             // one group of a step (16 shots per lane)
+  static const int PLANE_WORDS = BLOCKS * 32 * 32;
+  static const int WARP_WORDS = RAW_WORDS + PLANE_WORDS;    // shared memory per warp (words)
+};
+
+#ifndef QCUT_HOST_EMU
+QCUT_DEV void qcut_syncwarp() { __syncwarp(); }
+#else
+QCUT_DEV void qcut_syncwarp() {}
+#endif
+
+template <int NB, class Terms>
+QCUT_DEV void qcut_lane_tile_wide(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns,
+                                  int lane, uint32_t* acc, uint32_t* raw, uint32_t* planes) {
+  typedef QcutGeo<NB> G;
+  typedef QcutWide<NB> W;
+#pragma unroll
+  for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+  uint32_t* __restrict__ col = planes + lane;  // this lane's column of the row / plane store: col[slot * 32]
+  for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    const uint8_t* __restrict__ obs_s = obs + (uint64_t)s0 * NB;
+    const uint8_t* __restrict__ qpd_s = qpd + (uint64_t)s0 * nbq;
+    const bool full = n == G::STEP_SHOTS;
+
+    // ---- (1) qpd parity plane (same grouped geometry as the 3/5/6/7-byte rows) ----
+    uint32_t qp[1];
+    {
+      const QcutSrcGlobal src = {obs_s, qpd_s};
+      if (nbq == 1) {
+        uint32_t qraw[G::QRAW];
+        if (full) qcut_qpd_loads<NB, true, QcutSrcGlobal>(src, n, lane, qraw);
+        else qcut_qpd_loads<NB, false, QcutSrcGlobal>(src, n, lane, qraw);
+        qcut_qpd_planes<NB>(qraw, qp);
+      } else {
+        qp[0] = 0;
+        qcut_qp_slow<NB>(qpd_s, nbq, n, lane, qp);
+      }
+    }
+    uint32_t valid_rows = 0xFFFFFFFFu;
+    if (!full) {
+      valid_rows = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) valid_rows |= (uint32_t)(qcut_shot_of<NB>(j, 0, lane) < n) << j;
+      qp[0] &= valid_rows;
+    }
+
+    // ---- (2) per group: raw bytes -> shared memory (coalesced), then cut this lane's 16 rows of every
+    //      block out of its slot and store them in its column of the row store ----
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      qcut_syncwarp();  // readers of raw[] (previous group / step) are done
+#ifndef QCUT_HOST_EMU
+      {
+        const int region_bytes = 512 * NB;  // 32 lanes x 16 shots x NB bytes
+        int valid = n * NB - g * region_bytes;
+        valid = valid < 0 ? 0 : (valid > region_bytes ? region_bytes : valid);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          const int q = c * 32 + lane;  // 16-byte chunk of the region
+          qcut_u4 v = {0u, 0u, 0u, 0u};
+          if (q * 16 < valid) v = qcut_ld16(obs_s + (uint64_t)g * region_bytes + (uint64_t)q * 16);
+          const int owner = q / NB, pos = q - owner * NB;
+          uint32_t* dst = raw + owner * W::RAW_STRIDE + pos * 4;
+          dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+      }
+#else
+      {  // emulation runs one lane at a time: the lane copies its own group
+        uint32_t* dst = raw + lane * W::RAW_STRIDE;
+        for (int w = 0; w < 4 * NB; ++w) dst[w] = 0;
+        const int first = (g * 32 + lane) * 16;
+        if (first < n) {
+          int bytes = ((n - first < 16 ? n - first : 16) * NB + 15) & ~15;  // whole 16-byte chunks, as on the device
+          if (bytes > 16 * NB) bytes = 16 * NB;
+          memcpy(dst, obs_s + (uint64_t)first * NB, bytes);
+        }
+      }
+#endif
+      qcut_syncwarp();
+      const uint32_t* __restrict__ mine = raw + lane * W::RAW_STRIDE;
+#pragma unroll
+      for (int blk = 0; blk < W::BLOCKS; ++blk)
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int o = r * NB + 4 * blk;  // byte offset of this row word inside the lane's group
+          const int wi = o >> 2, sh = o & 3;
+          const uint32_t lo = mine[wi];
+          uint32_t row = sh == 0 ? lo : __byte_perm(lo, mine[wi + 1], 0x3210 + 0x1111 * sh);
+          if (!full && !((valid_rows >> (16 * g + r)) & 1u)) row = 0;  // rows past the end of the PUB
+          col[(blk * 32 + 16 * g + r) * 32] = row;
+        }
+    }
+
+    // ---- (3) block by block, in place: 32 rows -> 32 bit-planes (the column is private to the lane) ----
+#pragma unroll
+    for (int blk = 0; blk < W::BLOCKS; ++blk) {
+      uint32_t a[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = col[(blk * 32 + j) * 32];
+      qcut_transpose32(a);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) col[(blk * 32 + i) * 32] = a[i];
+    }
+
+    // ---- (4) XOR networks on planes read from shared memory at static offsets ----
+    Terms::run(col, col, qp[0], acc);
+  }
+}
+
 // ---- term engine B: run-time masks, bit-planes parked in shared memory -------------------------
 // planes[p * 32] is this lane's word of memory-bit plane p (the caller passes the lane's column).
 // mask words are the little-endian words of the mask row in memory order (plan table).

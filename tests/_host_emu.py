@@ -70,6 +70,8 @@ def emulate_tallies(tables, data: np.ndarray, engine: str = "jit") -> tuple[np.n
     """
     tallies = np.zeros(max(tables.n_tallies, 1), dtype=np.int64)
     sources = {g: _lib.generate_source(tables.groups, tables.masks, g) for g in range(len(tables.groups))}
+    if engine == "rt":  # the run-time-mask kernel covers rows of up to 8 bytes
+        sources = {g: (src if int(tables.groups[g]["nb_obs"]) <= 8 else "") for g, src in sources.items()}
     covered = np.array([bool(sources[int(g)]) for g in tables.pubs["group"]], dtype=bool)
     emus = {g: compile_emulator(src) for g, src in sources.items() if src}
     odd = np.zeros(4096, dtype=np.uint32)

@@ -27,7 +27,8 @@ def _run(tables, data, flags):
 
 
 @pytest.mark.parametrize("name,scale", [("cfg4_heavy_hex", 0.1), ("cfg5_molecular", 0.15), ("cfg3_wide_dense", 0.3),
-                                        ("cfg3_wide_local", 1.0), ("cfg2_wire", 1.0), ("cfg1_tutorial", 1.0)])
+                                        ("cfg3_wide_local", 1.0), ("cfg2_wire", 1.0), ("cfg1_tutorial", 1.0),
+                                        ("cfg4u_heavy_hex_unpartitioned", 0.02)])
 def test_three_kernels_agree_and_match_oracle_subsample(lib, name, scale):
     w = W.get_workload(name, scale)
     tables = W.build_tables(w)

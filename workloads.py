@@ -200,6 +200,13 @@ def get_workload(name: str, scale: float = 1.0) -> Workload:
     if name == "cfg4_heavy_hex":
         return Workload(name, "configs[3] 127-qubit heavy-hex in 2 halves, 8 cut CNOTs, ~10^5 sampled tuples",
                         observables_heavy_hex(), c(97_000), 8192, 8, 6561.0, 404)
+    if name == "cfg4u_heavy_hex_unpartitioned":
+        # not a BASELINE.json config: the same 127-qubit observables with the circuit NOT separated (call form 1 of
+        # the reference): one subsystem, 16-byte observable rows, one group of 271 terms -> wide-row kernel
+        n = 127
+        labels = [_z_string(n, [qb]) for qb in range(n)] + [_z_string(n, e) for e in heavy_hex_127_edges()]
+        return Workload(name, "extra: configs[3] observables, un-partitioned (16-byte rows)", {"A": PauliList(labels)},
+                        c(48_000), 8192, 8, 6561.0, 414)
     if name == "cfg5_molecular":
         w = Workload(name, "configs[4] 1000-term Hamiltonian, 4 subsystems, 10^4 subexperiments x 10^5 shots",
                      observables_molecular(), 1, 100_000, 4, 81.0, 505)
@@ -209,7 +216,8 @@ def get_workload(name: str, scale: float = 1.0) -> Workload:
     raise KeyError(name)
 
 
-WORKLOADS = ["cfg1_tutorial", "cfg2_wire", "cfg3_wide_dense", "cfg3_wide_local", "cfg4_heavy_hex", "cfg5_molecular"]
+WORKLOADS = ["cfg1_tutorial", "cfg2_wire", "cfg3_wide_dense", "cfg3_wide_local", "cfg4_heavy_hex", "cfg5_molecular",
+             "cfg4u_heavy_hex_unpartitioned"]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@ except Exception as e:
     print("$name: failed", e); print(open("$OUT/tune_$name.err").read()[-600:])
 PY
 }
-FLAGS=0 run direct QCUT_JIT_PREFETCH=0
-WL=cfg3_wide_dense SCALE=1 FLAGS=0 run dense QCUT_JIT_PREFETCH=0
-WL=cfg3_wide_local SCALE=1 FLAGS=0 run local QCUT_JIT_PREFETCH=0
+FLAGS=0 run base_256x2 QCUT_JIT_THREADS=256 QCUT_JIT_MINBLOCKS=2
+FLAGS=0 run t128x5 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=5
+FLAGS=0 run t128x6 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=6
+FLAGS=0 run t192x3 QCUT_JIT_THREADS=192 QCUT_JIT_MINBLOCKS=3
+FLAGS=0 run t64x9 QCUT_JIT_THREADS=64 QCUT_JIT_MINBLOCKS=9

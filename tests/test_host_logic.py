@@ -1,0 +1,80 @@
+"""Host logic without a GPU: grouping invariants (property based), mask layout, install(), staged-size accounting."""
+
+import sys
+import types
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle
+from qiskit_addon_cutting_b200 import PauliList, install, reconstruct_expectation_values
+from qiskit_addon_cutting_b200.observable_grouping import CommutingObservableGroup, ObservableCollection, most_general_observable
+
+labels = st.integers(1, 9).flatmap(
+    lambda n: st.lists(st.text(alphabet="IXYZ", min_size=n, max_size=n), min_size=1, max_size=14)
+)
+
+
+@settings(max_examples=120, deadline=None)
+@given(labels)
+def test_grouping_invariants(obs_labels):
+    paulis = PauliList(obs_labels)
+    coll = ObservableCollection(paulis)
+    seen = {}
+    for gi, cog in enumerate(coll.groups):
+        members = cog.commuting_observables
+        # every member is measurable from the general observable: same Pauli wherever the member is non-identity
+        gz, gx = np.asarray(cog.general_observable.z), np.asarray(cog.general_observable.x)
+        for ti, m in enumerate(members):
+            non_i = np.asarray(m.z) | np.asarray(m.x)
+            assert np.all(np.asarray(m.z)[non_i] == gz[non_i]) and np.all(np.asarray(m.x)[non_i] == gx[non_i])
+            assert m.to_label() not in seen, "an observable sits in exactly one group"
+            seen[m.to_label()] = (gi, ti)
+            # mask bit i <-> qubit pauli_indices[i]
+            expect = sum(1 << i for i, q in enumerate(cog.pauli_indices) if non_i[q])
+            assert cog.pauli_bitmasks[ti] == expect
+        assert cog.pauli_indices == sorted(cog.pauli_indices)
+        assert set(cog.pauli_indices) == set(np.flatnonzero(gz | gx).tolist())
+    assert set(seen) == set(obs_labels)
+    for k, lab in enumerate(obs_labels):
+        assert coll.lookup_indices[k] == [seen[lab]]
+    # the oracle's pure-Python grouping (reference loops) agrees with the vectorised one
+    oc = oracle.build_collection(paulis)
+    assert [g["masks"] for g in oc["groups"]] == [c.pauli_bitmasks for c in coll.groups]
+    assert [g["pauli_indices"] for g in oc["groups"]] == [c.pauli_indices for c in coll.groups]
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 70), st.integers(0, 2**70 - 1), st.integers(1, 12))
+def test_mask_bytes_are_big_endian_rows(nbits, value, nbytes):
+    cog = CommutingObservableGroup.__new__(CommutingObservableGroup)
+    object.__setattr__(cog, "pauli_bitmasks", [value & ((1 << nbits) - 1)])
+    rows = cog.mask_bytes(nbytes)
+    assert rows.shape == (1, nbytes)
+    assert int.from_bytes(rows[0].tobytes(), "big") == (value & ((1 << nbits) - 1)) & ((1 << (8 * nbytes)) - 1)
+
+
+def test_most_general_observable_matches_reference_docstring_and_errors():
+    assert most_general_observable(PauliList(["IIIZ", "IIZZ", "XIII"])).to_label() == "XIZZ"  # observable_grouping.py:77-78
+    with pytest.raises(ValueError, match="Empty input sequence"):
+        most_general_observable([])
+    with pytest.raises(ValueError, match="Observables are incompatible"):
+        most_general_observable(PauliList(["X", "Z"]))
+    with pytest.raises(ValueError, match="incorrect qubit count"):
+        most_general_observable(list(PauliList(["XX"])) + list(PauliList(["X"])))
+    with pytest.raises(ValueError, match="only supports Paulis with phase == 0"):
+        CommutingObservableGroup(PauliList(["ZZ"])[0], list(PauliList(["iZZ"])))
+
+
+def test_install_patches_the_reference_when_importable(monkeypatch):
+    assert install() is False  # the reference is not installed in this image
+    pkg = types.ModuleType("qiskit_addon_cutting")
+    sub = types.ModuleType("qiskit_addon_cutting.cutting_reconstruction")
+    sub.reconstruct_expectation_values = pkg.reconstruct_expectation_values = lambda *a, **k: "reference"
+    pkg.cutting_reconstruction = sub
+    monkeypatch.setitem(sys.modules, "qiskit_addon_cutting", pkg)
+    monkeypatch.setitem(sys.modules, "qiskit_addon_cutting.cutting_reconstruction", sub)
+    assert install() is True
+    assert pkg.reconstruct_expectation_values is reconstruct_expectation_values
+    assert sub.reconstruct_expectation_values is reconstruct_expectation_values

@@ -189,8 +189,7 @@ def ours_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if rank == 0:
-        entry.build_library()
+    entry.build_library()  # serialised across ranks by a file lock; a no-op when the library is current
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL announces its version on stdout at communicator creation; the contract is ONE JSON line on

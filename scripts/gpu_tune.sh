@@ -16,8 +16,8 @@ except Exception as e:
     print("$name: failed", e); print(open("$OUT/tune_$name.err").read()[-600:])
 PY
 }
-FLAGS=0 run base_256x2 QCUT_JIT_THREADS=256 QCUT_JIT_MINBLOCKS=2
-FLAGS=0 run t128x5 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=5
-FLAGS=0 run t128x6 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=6
-FLAGS=0 run t192x3 QCUT_JIT_THREADS=192 QCUT_JIT_MINBLOCKS=3
-FLAGS=0 run t64x9 QCUT_JIT_THREADS=64 QCUT_JIT_MINBLOCKS=9
+FLAGS=0 run base QCUT_JIT_PREFETCH=0
+FLAGS=0 run pf1 QCUT_JIT_PREFETCH=1
+FLAGS=0 run pf2 QCUT_JIT_PREFETCH=2
+FLAGS=4 run staged QCUT_JIT_PREFETCH=0
+FLAGS=4 run staged_128x4 QCUT_JIT_THREADS=128 QCUT_JIT_MINBLOCKS=4

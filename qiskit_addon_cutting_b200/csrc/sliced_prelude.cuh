@@ -256,8 +256,9 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
       const bool valid = FULL || (g * 32 + lane) * 16 < n;
 #pragma unroll
       for (int c = 0; c < NB; ++c) {
-        qcut_u4 v = {0u, 0u, 0u, 0u};
-        if (valid) v = src.obs16_shared_sectors((g * 32 + lane) * 16 * NB + c * 16);
+        // tail steps: clamp the address instead of predicating the load (predicated loads issue one
+        // at a time); whatever an out-of-range lane reads is zeroed by qcut_mask_tail
+        const qcut_u4 v = src.obs16_shared_sectors(valid ? (g * 32 + lane) * 16 * NB + c * 16 : 0);
         w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
       }
       w[4 * NB] = 0;
@@ -274,8 +275,7 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
   } else {
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
-      qcut_u4 v = {0u, 0u, 0u, 0u};
-      if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
+      const qcut_u4 v = src.obs16((FULL || (k * 32 + lane) * G::SPC < n) ? lane * 16 + k * 512 : 0);
       if constexpr (NB == 8) {
         a[0][2 * k] = v.x; a[1][2 * k] = v.y;
         a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
@@ -297,15 +297,13 @@ QCUT_DEV void qcut_qpd_loads(const Src src, int n, int lane, uint32_t* qraw) {
     // group g: the 16 qpd bytes of shots 16*(32g+lane) .. +15 -> words 4g .. 4g+3 (rows 16g+4w .. +3)
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      qcut_u4 v = {0u, 0u, 0u, 0u};
-      if (FULL || (g * 32 + lane) * 16 < n) v = src.qpd16((g * 32 + lane) * 16);
+      const qcut_u4 v = src.qpd16((FULL || (g * 32 + lane) * 16 < n) ? (g * 32 + lane) * 16 : 0);
       qraw[4 * g] = v.x; qraw[4 * g + 1] = v.y; qraw[4 * g + 2] = v.z; qraw[4 * g + 3] = v.w;
     }
   } else if constexpr (NB == 1) {
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
-      qcut_u4 v = {0u, 0u, 0u, 0u};
-      if (FULL || (k * 32 + lane) * G::SPC < n) v = src.qpd16(lane * 16 + k * 512);
+      const qcut_u4 v = src.qpd16((FULL || (k * 32 + lane) * G::SPC < n) ? lane * 16 + k * 512 : 0);
       qraw[4 * k] = v.x; qraw[4 * k + 1] = v.y; qraw[4 * k + 2] = v.z; qraw[4 * k + 3] = v.w;
     }
   } else {
@@ -315,20 +313,15 @@ QCUT_DEV void qcut_qpd_loads(const Src src, int n, int lane, uint32_t* qraw) {
       const int idx = k * 32 + lane;
       if constexpr (NB == 8) {
         if (k & 1) continue;  // chunks k, k+1 -> rows 2k .. 2k+3
-        uint32_t w = 0;
-        if (FULL || idx * 2 < n) w = src.qpd2(ql + k * 64);
-        if (FULL || (idx + 32) * 2 < n) w |= src.qpd2(ql + (k + 1) * 64) << 16;
+        uint32_t w = src.qpd2((FULL || idx * 2 < n) ? ql + k * 64 : 0);
+        w |= src.qpd2((FULL || (idx + 32) * 2 < n) ? ql + (k + 1) * 64 : 0) << 16;
         qraw[k / 2] = w;
       } else if constexpr (NB == 4) {
-        uint32_t w = 0;
-        if (FULL || idx * 4 < n) w = src.qpd4(ql + k * 128);
-        qraw[k] = w;
+        qraw[k] = src.qpd4((FULL || idx * 4 < n) ? ql + k * 128 : 0);
       } else {  // NB == 2
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          uint32_t w = 0;
-          if (FULL || idx * 8 + 4 * h < n) w = src.qpd4(ql + k * 256 + 4 * h);
-          qraw[2 * k + h] = w;
+          qraw[2 * k + h] = src.qpd4((FULL || idx * 8 + 4 * h < n) ? ql + k * 256 + 4 * h : 0);
         }
       }
     }
@@ -507,16 +500,26 @@ QCUT_DEV void qcut_lane_tile_wide(const uint8_t* __restrict__ obs, const uint8_t
 #ifndef QCUT_HOST_EMU
       {
         const int region_bytes = 512 * NB;  // 32 lanes x 16 shots x NB bytes
-        int valid = n * NB - g * region_bytes;
-        valid = valid < 0 ? 0 : (valid > region_bytes ? region_bytes : valid);
+        const uint8_t* __restrict__ src = obs_s + (uint64_t)g * region_bytes + (uint64_t)lane * 16;
+        qcut_u4 v[NB];
+        if (full) {
+          // all NB loads are issued back to back (no predicate between a load and its use)
+#pragma unroll
+          for (int c = 0; c < NB; ++c) v[c] = qcut_ld16(src + c * 512);
+        } else {
+          int valid = n * NB - g * region_bytes;
+          valid = valid < 0 ? 0 : (valid > region_bytes ? region_bytes : valid);
+#pragma unroll
+          for (int c = 0; c < NB; ++c)  // clamped address, not a predicate: the loads stay back to back;
+                                        // chunks past the end only feed rows that valid_rows zeroes
+            v[c] = qcut_ld16((c * 32 + lane) * 16 < valid ? src + c * 512 : obs_s);
+        }
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
           const int q = c * 32 + lane;  // 16-byte chunk of the region
-          qcut_u4 v = {0u, 0u, 0u, 0u};
-          if (q * 16 < valid) v = qcut_ld16(obs_s + (uint64_t)g * region_bytes + (uint64_t)q * 16);
           const int owner = q / NB, pos = q - owner * NB;
           uint32_t* dst = raw + owner * W::RAW_STRIDE + pos * 4;
-          dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+          dst[0] = v[c].x; dst[1] = v[c].y; dst[2] = v[c].z; dst[3] = v[c].w;
         }
       }
 #else

@@ -71,6 +71,25 @@ def _outcome_to_int(outcome) -> int:
     return int(outcome, 0)
 
 
+_collection_cache: dict = {}
+
+
+def _collection(observables) -> ObservableCollection:
+    """``ObservableCollection(observables)`` (reference ``:113-116``), memoised on the Pauli content.
+
+    Grouping is a pure function of the (phase-free) symplectic rows, and repeated reconstructions of one cut
+    circuit pass the same observables; the plan cache in ``engine`` is keyed the same way.
+    """
+    z, x = np.asarray(observables.z, dtype=bool), np.asarray(observables.x, dtype=bool)
+    key = (type(observables), z.shape, z.tobytes(), x.tobytes())
+    hit = _collection_cache.get(key)
+    if hit is None:
+        if len(_collection_cache) >= 16:
+            _collection_cache.pop(next(iter(_collection_cache)))
+        hit = _collection_cache[key] = ObservableCollection(observables)
+    return hit
+
+
 def _normalise(results, observables):
     """Validation and dict normalisation, in the reference's order (``:79-111``)."""
     if _is_pauli_list(observables):
@@ -124,7 +143,7 @@ def reconstruct_expectation_values(
     """
     subobservables, results_dict, n_obs = _normalise(results, observables)
 
-    collections = {label: ObservableCollection(obs) for label, obs in subobservables.items()}
+    collections = {label: _collection(obs) for label, obs in subobservables.items()}
 
     # len(results) == len(coefficients) * len(groups) for every subsystem (reference :120-131)
     for label, so in collections.items():

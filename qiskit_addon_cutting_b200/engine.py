@@ -12,6 +12,7 @@ Terminology follows the reference: a *PUB* is the result of one subexperiment
 from __future__ import annotations
 
 import ctypes as C
+import queue
 import threading
 from dataclasses import dataclass, field
 
@@ -367,53 +368,78 @@ class HostArrays:
 
 
 def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int,
-                      n_obs: int) -> tuple[HostTables, HostArrays]:
+                      n_obs: int, *, sink=None, block_pubs: int = 0) -> tuple[HostTables, HostArrays]:
     """Walk the PUBs of coefficient range ``[i_lo, i_hi)`` of every label (host only, no device).
 
-    Offsets, tally slots and group variants are computed with NumPy, not per PUB.
+    Offsets, tally slots and group variants are computed with NumPy, not per PUB.  The walk proceeds in
+    blocks of ``block_pubs`` PUBs (0: one block per label; with a sink the blocks of a label grow 4x each).  Without ``sink`` the blocks are laid out back to
+    back in one staging buffer.  With ``sink`` every block is handed over as soon as it has been walked
+    (``sink(src, nbytes, dst, block_bytes)`` returns the block's byte offset from a base address the sink
+    fixes later through ``sink.rebase()``): staging of block b overlaps the walk of block b+1.
     """
     builder = TableBuilder(n_obs)
     keep_all: list = []
-    src_chunks, nbytes_chunks, dst_chunks, chunks = [], [], [], []
+    src_chunks, nbytes_chunks, dst_chunks, chunks, bases = [], [], [], [], []
     offset = 0
     tally_offset = 0
     n_pubs = 0
     for result, collection in zip(results_by_label, collections):
         n_groups = len(collection.groups)
         li = builder.add_label(collection, n_pubs)
-        keep, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd = _collect_label(result, i_lo * n_groups, i_hi * n_groups)
-        n = len(shots)
-        g_idx = np.tile(np.arange(n_groups), i_hi - i_lo) if n else np.zeros(0, dtype=np.int64)
-        # group variants: one per distinct (group, row width)
-        variant = np.empty(n, dtype=np.uint32)
-        for g, nb in {(int(g), int(nb)) for g, nb in zip(g_idx.tolist(), nb_obs.tolist())}:
-            variant[(g_idx == g) & (nb_obs == nb)] = builder.group_variant(li, g, nb)
-        terms = np.array([builder.n_terms(li, g) for g in range(n_groups)], dtype=np.int64)[g_idx] if n else np.zeros(0, dtype=np.int64)
-        raw = np.empty(2 * n, dtype=np.int64)
-        raw[0::2] = shots * nb_obs
-        raw[1::2] = shots * nb_qpd
-        sizes = (raw + _ALIGN - 1) // _ALIGN * _ALIGN
-        starts = offset + np.concatenate([[0], np.cumsum(sizes)[:-1]]) if n else np.zeros(0, dtype=np.int64)
-        pubs = np.zeros(n, dtype=PUB_DTYPE)
-        pubs["obs_offset"] = starts[0::2]
-        pubs["qpd_offset"] = starts[1::2]
-        pubs["tally_offset"] = tally_offset + (np.concatenate([[0], np.cumsum(terms)[:-1]]) if n else 0)
-        pubs["shots"] = shots
-        pubs["group"] = variant
-        pubs["nb_qpd"] = nb_qpd
-        if n and int(shots.max()) >= 2**31:
-            raise ValueError("A PUB with 2**31 or more shots is not supported.")
-        src = np.empty(2 * n, dtype=np.uint64)
-        src[0::2] = obs_ptr
-        src[1::2] = qpd_ptr
-        src_chunks.append(src)
-        nbytes_chunks.append(raw.astype(np.uint64))
-        dst_chunks.append(starts.astype(np.uint64))
-        offset += int(sizes.sum())
-        tally_offset += int(terms.sum())
-        n_pubs += n
-        chunks.append(pubs)
-        keep_all.extend(keep)
+        terms_of_group = np.array([builder.n_terms(li, g) for g in range(n_groups)], dtype=np.int64)
+        p_lo, p_hi = i_lo * n_groups, i_hi * n_groups
+        step = block_pubs if block_pubs > 0 else max(p_hi - p_lo, 1)
+        b_hi = p_lo
+        while b_hi < p_hi:
+            b_lo, b_hi = b_hi, min(b_hi + step, p_hi)
+            if sink is not None:
+                step *= 4  # every hand-over costs the sink a pipeline fill: few, growing blocks
+            keep, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd = _collect_label(result, b_lo, b_hi)
+            n = b_hi - b_lo
+            g_idx = np.arange(b_lo, b_hi, dtype=np.int64) % n_groups
+            # group variants: one per distinct (group, row width)
+            variant = np.empty(n, dtype=np.uint32)
+            key = (g_idx << 32) + nb_obs
+            for k in np.unique(key).tolist():
+                variant[key == k] = builder.group_variant(li, k >> 32, k & 0xFFFFFFFF)
+            terms = terms_of_group[g_idx]
+            if int(shots.max()) >= 2**31:
+                raise ValueError("A PUB with 2**31 or more shots is not supported.")
+            raw = np.empty(2 * n, dtype=np.int64)
+            raw[0::2] = shots * nb_obs
+            raw[1::2] = shots * nb_qpd
+            sizes = (raw + _ALIGN - 1) // _ALIGN * _ALIGN
+            starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+            block_bytes = int(sizes.sum())
+            src = np.empty(2 * n, dtype=np.uint64)
+            src[0::2] = obs_ptr
+            src[1::2] = qpd_ptr
+            nbytes = raw.astype(np.uint64)
+            if sink is None:
+                base = offset
+            else:
+                base = 0
+                bases.append(sink(src, nbytes, starts.astype(np.uint64), block_bytes))
+            pubs = np.zeros(n, dtype=PUB_DTYPE)
+            pubs["obs_offset"] = base + starts[0::2]
+            pubs["qpd_offset"] = base + starts[1::2]
+            pubs["tally_offset"] = tally_offset + np.concatenate([[0], np.cumsum(terms)[:-1]])
+            pubs["shots"] = shots
+            pubs["group"] = variant
+            pubs["nb_qpd"] = nb_qpd
+            src_chunks.append(src)
+            nbytes_chunks.append(nbytes)
+            dst_chunks.append((base + starts).astype(np.uint64))
+            offset += block_bytes
+            tally_offset += int(terms.sum())
+            n_pubs += n
+            chunks.append(pubs)
+            keep_all.extend(keep)
+    if sink is not None:
+        # the blocks live in separate device allocations: make every offset relative to the lowest one
+        for pubs, delta in zip(chunks, sink.rebase(bases)):
+            pubs["obs_offset"] += np.uint64(delta)
+            pubs["qpd_offset"] += np.uint64(delta)
     pubs = np.concatenate(chunks) if chunks else np.zeros(0, dtype=PUB_DTYPE)
     cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint64)  # noqa: E731
     arrays = HostArrays(keep_all, cat(src_chunks), cat(nbytes_chunks), cat(dst_chunks))
@@ -433,26 +459,91 @@ def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_thread
 
 
 _STAGING_BYTES = 256 << 20  # pinned staging ring for the end-to-end path, independent of the problem size
+_BLOCK_PUBS = 2048  # PUBs in the first staging block of a label (~1 ms of attribute walk); later blocks grow 4x
+
+
+class _BlockStager:
+    """Background staging of walked blocks: one thread feeds ``qcut_stage_h2d`` while the caller keeps walking.
+
+    Every block gets its own device allocation (its size is only known once it has been walked); ``rebase``
+    turns the block addresses into offsets from the lowest one, which becomes the kernels' ``d_data``.
+    The ctypes call releases the GIL, so the gather + PCIe transfer of block b run beside the C-API walk of
+    block b+1.  Copies are queued on the stream that was current when the stager was created.
+    """
+
+    def __init__(self):
+        self.device = torch.cuda.current_device()
+        self.stream = _stream_ptr()
+        self.pinned = _pinned_buffer(_STAGING_BYTES)
+        self.blocks: list[torch.Tensor] = []
+        self.base = 0
+        self.error: BaseException | None = None
+        self.queue: queue.SimpleQueue = queue.SimpleQueue()
+        self.thread = threading.Thread(target=self._run, name="qcut-stage", daemon=True)
+        self.thread.start()
+
+    def __call__(self, src: np.ndarray, nbytes: np.ndarray, dst: np.ndarray, block_bytes: int) -> int:
+        block = torch.empty(block_bytes + _lib.DATA_SLACK, dtype=torch.uint8, device="cuda")
+        self.blocks.append(block)
+        if len(src):
+            self.queue.put((src, nbytes, dst, block.data_ptr()))
+        return block.data_ptr()
+
+    def rebase(self, addresses: list[int]) -> list[int]:
+        self.base = min(addresses) if addresses else 0
+        return [a - self.base for a in addresses]
+
+    def _run(self) -> None:
+        try:
+            torch.cuda.set_device(self.device)  # qcut_stage_h2d copies to the calling thread's device
+            lib = _lib.load()
+            while True:
+                item = self.queue.get()
+                if item is None:
+                    return
+                if self.error is not None:
+                    continue  # drain
+                src, nbytes, dst, d_ptr = item
+                check(
+                    lib.qcut_stage_h2d(_lib.np_ptr(src), _lib.np_ptr(nbytes), _lib.np_ptr(dst), len(src),
+                                       self.pinned.data_ptr(), self.pinned.numel(), d_ptr, 0, self.stream),
+                    "qcut_stage_h2d",
+                )
+        except BaseException as ex:  # noqa: BLE001 - re-raised on the caller's thread by finish()
+            self.error = ex
+
+    def finish(self, *, raise_errors: bool = True) -> None:
+        """Wait until every queued block is in HBM (``qcut_stage_h2d`` returns after its last copy)."""
+        self.queue.put(None)
+        self.thread.join()
+        if raise_errors and self.error is not None:
+            raise self.error
+
+    def data_ptr(self) -> int:
+        return self.base
 
 
 def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
              *, flags: int = 0) -> DeviceBatch:
     """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM.
 
-    Worker threads gather runs of borrowed ``BitArray`` buffers into a small pinned ring and queue one H2D
-    copy per run on the current stream (``qcut_stage_h2d``): the host gather overlaps the PCIe transfer.
+    The PUBs are walked block by block (``csrc/pyhelper.c``); a background thread hands every walked block to
+    ``qcut_stage_h2d``, whose worker threads gather runs of borrowed ``BitArray`` buffers into a small pinned
+    ring and queue one H2D copy per run: attribute walk, host gather and PCIe transfer all overlap.
     """
     _lib.require_device()
-    tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs)
-    total = tables.data_bytes
-    data = torch.empty(total + _lib.DATA_SLACK, dtype=torch.uint8, device="cuda")
-    if len(arrays):
-        pinned = _pinned_buffer(_STAGING_BYTES)
-        check(
-            _lib.load().qcut_stage_h2d(
-                _lib.np_ptr(arrays.src), _lib.np_ptr(arrays.nbytes), _lib.np_ptr(arrays.dst), len(arrays),
-                pinned.data_ptr(), pinned.numel(), data.data_ptr(), 0, _stream_ptr(),
-            ),
-            "qcut_stage_h2d",
-        )
-    return DeviceBatch(tables, data, flags=flags)
+    stager = _BlockStager()
+    try:
+        tables, _ = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, sink=stager,
+                                      block_pubs=_BLOCK_PUBS)
+    except BaseException:
+        stager.finish(raise_errors=False)
+        raise
+    # plan lookup / schedule upload proceed while the last blocks are still in flight
+    try:
+        batch = DeviceBatch(tables, stager, flags=flags)
+    finally:
+        stager.finish(raise_errors=False)
+    if stager.error is not None:
+        raise stager.error
+    return batch

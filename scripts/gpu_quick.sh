@@ -4,7 +4,9 @@ set -u
 OUT=gpurun_out
 mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build(); print('build ok')" > $OUT/build.log 2>&1 || { tail -30 $OUT/build.log; exit 1; }
+if [ "${TESTS:-1}" = "1" ]; then
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 $OUT/pytest_gpu.log
+fi
 for wl in ${WORKLOADS:-cfg4_heavy_hex cfg3_wide_dense cfg5_molecular cfg3_wide_local cfg2_wire}; do
   timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err
   echo "bench $wl exit $?"; python - <<PY

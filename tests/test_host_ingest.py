@@ -57,3 +57,60 @@ def test_non_conforming_arrays_take_the_slow_path(lib):
     short = {"A": PrimitiveResult([PubResult(DataBin(observable_measurements=Reg(base[:10]), qpd_measurements=Reg(qpd)))])}
     with pytest.raises(IndexError):
         _tables(short, coefficients, observables)
+
+
+@pytest.mark.parametrize("name", ["molecular", "odd_widths"])
+def test_blocked_walk_gives_the_same_tables(lib, name):
+    """Walking the PUBs in small blocks changes nothing in the tables or the staged layout."""
+    results, coefficients, observables = _cases.SMALL_CASES[name]()
+    labels = list(observables)
+    colls = [ObservableCollection(observables[label]) for label in labels]
+    coeffs = np.array([c for c, _ in coefficients], dtype=np.float64)
+    args = ([results[label] for label in labels], colls, coeffs, 0, len(coeffs), len(observables[labels[0]]))
+    whole, arrays_w = engine.build_host_tables(*args)
+    for block in (1, 3, 7):
+        tables, arrays = engine.build_host_tables(*args, block_pubs=block)
+        for f in ("groups", "masks", "pubs", "labels", "lookup_start", "lookup", "coeffs"):
+            assert np.array_equal(getattr(tables, f), getattr(whole, f)), (block, f)
+        assert (tables.n_tallies, tables.data_bytes) == (whole.n_tallies, whole.data_bytes)
+        assert np.array_equal(arrays.dst, arrays_w.dst) and np.array_equal(arrays.nbytes, arrays_w.nbytes)
+
+
+def test_block_sink_offsets_are_relative_to_the_lowest_block(lib):
+    """With a sink every block lands in its own allocation; PUB offsets are relative to the lowest address."""
+    results, coefficients, observables = _cases.SMALL_CASES["molecular"]()
+    labels = list(observables)
+    colls = [ObservableCollection(observables[label]) for label in labels]
+    coeffs = np.array([c for c, _ in coefficients], dtype=np.float64)
+
+    class Sink:
+        def __init__(self):
+            self.blocks, self.base = [], 0
+
+        def __call__(self, src, nbytes, dst, block_bytes):
+            # over-allocate by a varying amount so that the blocks are neither adjacent nor ordered by size
+            block = np.zeros(block_bytes + 64 * (1 + len(self.blocks) % 3), dtype=np.uint8)
+            self.blocks.append(block)
+            assert lib.qcut_gather_host(src.ctypes.data, nbytes.ctypes.data, dst.ctypes.data, len(src), block.ctypes.data, 1) == 0
+            return block.ctypes.data
+
+        def rebase(self, addresses):
+            self.base = min(addresses)
+            return [a - self.base for a in addresses]
+
+    sink = Sink()
+    tables, _ = engine.build_host_tables([results[label] for label in labels], colls, coeffs, 0, len(coeffs),
+                                         len(observables[labels[0]]), sink=sink, block_pubs=5)
+    assert len(sink.blocks) > len(labels)
+    # read every PUB back through base + offset and compare with the caller's arrays
+    import ctypes
+    idx = 0
+    for label, coll in zip(labels, colls):
+        for p in range(len(coeffs) * len(coll.groups)):
+            pub = tables.pubs[idx]
+            data = results[label][p].data
+            for off, reg in ((pub["obs_offset"], data.observable_measurements), (pub["qpd_offset"], data.qpd_measurements)):
+                want = np.ascontiguousarray(reg.array)
+                got = np.frombuffer((ctypes.c_uint8 * want.size).from_address(sink.base + int(off)), dtype=np.uint8)
+                assert np.array_equal(got, want.reshape(-1)), (label, p)
+            idx += 1

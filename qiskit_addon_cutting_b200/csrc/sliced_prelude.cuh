@@ -544,7 +544,6 @@ QCUT_DEV void qcut_lane_tile_wide(const uint8_t* __restrict__ obs, const uint8_t
           const int wi = o >> 2, sh = o & 3;
           const uint32_t lo = mine[wi];
           uint32_t row = sh == 0 ? lo : __byte_perm(lo, mine[wi + 1], 0x3210 + 0x1111 * sh);
-          if (!full && !((valid_rows >> (16 * g + r)) & 1u)) row = 0;  // rows past the end of the PUB
           col[(blk * 32 + 16 * g + r) * 32] = row;
         }
     }
@@ -556,6 +555,10 @@ QCUT_DEV void qcut_lane_tile_wide(const uint8_t* __restrict__ obs, const uint8_t
 #pragma unroll
       for (int j = 0; j < 32; ++j) a[j] = col[(blk * 32 + j) * 32];
       qcut_transpose32(a);
+      if (!full) {  // rows past the end of the PUB hold bytes of the padding / next matrix: drop their shots
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] &= valid_rows;
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) col[(blk * 32 + i) * 32] = a[i];
     }

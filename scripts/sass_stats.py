@@ -2,6 +2,7 @@
 
     python scripts/sass_stats.py cfg4_heavy_hex [group]
 """
+import re
 import subprocess
 import sys
 from collections import Counter
@@ -22,7 +23,7 @@ sass = subprocess.run(["cuobjdump", "-sass", "/tmp/qcut_k.cubin"], capture_outpu
 lines = []
 for ln in sass.splitlines():
     ln = ln.strip()
-    if ln.startswith("/*") and "*/" in ln[2:8]:
+    if re.match(r"/\*[0-9a-f]{4,}\*/", ln):
         body = ln.split("*/", 1)[1].split("/*")[0].strip().rstrip(";").strip()
         if body:
             lines.append(body)

@@ -166,6 +166,19 @@ int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_p
                                const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
                                void* d_workspace, int single_slot, void* stream);
 
+/* ---- term recombination (reference utils/observable_terms.py:60-90) ------------------------------
+ * The step right after the path: the expectation value of every observable (SparsePauliOp) is
+ *   out[r] = sum_{j in [d_row_start[r], d_row_start[r+1])} coeff[j] * e[d_term_index[j]]
+ * in complex fp64, accumulated sequentially in the order given, one separate multiply / add per
+ * operation (no FMA contraction): bit-identical to the reference's `rv += coeff * term_expval`
+ * loop.  d_coeffs and d_out are interleaved (re, im) pairs; d_term_expvals holds doubles
+ * (expvals_complex = 0: imaginary part +0.0, e.g. the output of qcut_reduce_launch, still in HBM)
+ * or interleaved pairs (expvals_complex = 1).  Terms with a zero coefficient are left out of
+ * the rows by the caller (reference :71-72). */
+int qcut_recombine_launch(const double* d_term_expvals, int expvals_complex,
+                          const uint32_t* d_row_start, const uint32_t* d_term_index,
+                          const double* d_coeffs, int n_rows, double* d_out, void* stream);
+
 /* ---- host staging: gather many borrowed BitArray buffers into one pinned buffer ---------------
  * Copies n_arrays host buffers (h_src[i], h_bytes[i] bytes) to h_dst + h_dst_offset[i] with
  * n_threads worker threads (0 = hardware concurrency).  Pure host code; used on the end-to-end

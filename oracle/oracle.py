@@ -282,3 +282,47 @@ def all_tallies(results, coefficients, observables) -> dict:
             )
         out[label] = tallies
     return out
+
+
+# ---- term recombination (reference utils/observable_terms.py:22-90) ------------------------------------
+_PHASE_FACTOR = (1 + 0j, -1j, -1 + 0j, 1j)  # (-i)**phase
+
+
+def _op_terms(observable):
+    """(phase-free key, coefficient) pairs of SparsePauliOp(observable) (reference :33-35,65-67)."""
+    if hasattr(observable, "paulis"):
+        return [(_key(p), c) for p, c in zip(observable.paulis, observable.coeffs, strict=True)]
+    return [(_key(observable), np.complex128(_PHASE_FACTOR[int(observable.phase) % 4]))]
+
+
+def unique_term_keys(observables) -> list:
+    """Keys of ``gather_unique_observable_terms`` in its order (reference :30-41): first appearance, zero
+    coefficients skipped."""
+    seen, out = set(), []
+    for observable in observables:
+        for key, coeff in _op_terms(observable):
+            if coeff == 0:
+                continue
+            if key not in seen:
+                seen.add(key)
+                out.append(key)
+    return out
+
+
+def observable_expvals_from_terms(observables, term_expvals: Mapping) -> list:
+    """Literal restatement of reference :60-90: ``rv = 0.0j; rv += coeff * term_expval`` per term, in order.
+
+    ``term_expvals`` maps Paulis (phase-free) to numbers; a missing term raises the reference's ValueError.
+    """
+    table = {_key(p): v for p, v in term_expvals.items()}
+    out = []
+    for observable in observables:
+        rv = 0.0j
+        for key, coeff in _op_terms(observable):
+            if coeff == 0:
+                continue
+            if key not in table:
+                raise ValueError("An observable contains a Pauli term whose expectation value was not provided.")
+            rv += coeff * table[key]
+        out.append(rv)
+    return out

@@ -9,14 +9,24 @@ from .containers import (
     PubResult,
     QuasiDistribution,
     SamplerResult,
+    SparsePauliOp,
     WeightType,
 )
 from .cutting_reconstruction import reconstruct_expectation_values
 from .observable_grouping import CommutingObservableGroup, ObservableCollection
+from .observable_terms import (
+    TermRecombination,
+    gather_unique_observable_terms,
+    reconstruct_observable_expvals_from_terms,
+)
 
 __all__ = [
     "reconstruct_expectation_values",
     "install",
+    "gather_unique_observable_terms",
+    "reconstruct_observable_expvals_from_terms",
+    "TermRecombination",
+    "SparsePauliOp",
     "CommutingObservableGroup",
     "ObservableCollection",
     "WeightType",

@@ -34,6 +34,7 @@ __all__ = [
     "WeightType",
     "Pauli",
     "PauliList",
+    "SparsePauliOp",
     "BitArray",
     "DataBin",
     "PubResult",
@@ -180,6 +181,9 @@ class PauliList:
         for i in range(len(self)):
             yield self[i]
 
+    def copy(self) -> "PauliList":
+        return PauliList(self)
+
     def to_labels(self) -> list[str]:
         return [p.to_label() for p in self]
 
@@ -245,6 +249,53 @@ class PauliList:
         for node, c in colour.items():
             groups[c].append(node)
         return [self[g] for g in groups.values()]
+
+
+_PHASE_FACTOR = np.array([1, -1j, -1, 1j], dtype=np.complex128)  # (-i)**phase
+
+
+class SparsePauliOp:
+    """Linear combination of phase-free Paulis: ``sum_j coeffs[j] * paulis[j]`` (Qiskit ``SparsePauliOp`` protocol).
+
+    Only what the term-recombination step touches (reference ``utils/observable_terms.py:22-90``):
+    ``.paulis`` (phases absorbed into ``.coeffs``, as Qiskit does), ``.coeffs`` (complex128),
+    ``.num_qubits``, ``len()`` and iteration over single-term operators.
+    """
+
+    def __init__(self, data, coeffs=None):
+        if isinstance(data, SparsePauliOp):
+            self.paulis = PauliList(data.paulis)
+            self.coeffs = data.coeffs.copy() if coeffs is None else np.asarray(coeffs, dtype=np.complex128).copy()
+            return
+        pl = data if isinstance(data, PauliList) else PauliList(data)
+        c = np.ones(len(pl), dtype=np.complex128) if coeffs is None else np.asarray(coeffs, dtype=np.complex128)
+        if c.shape != (len(pl),):
+            raise ValueError("coeff vector is incorrect shape for number of Paulis")
+        self.coeffs = _PHASE_FACTOR[pl.phase] * c
+        self.paulis = PauliList.from_symplectic(pl.z, pl.x, 0)
+
+    @property
+    def num_qubits(self) -> int:
+        return self.paulis.num_qubits
+
+    @property
+    def size(self) -> int:
+        return len(self.paulis)
+
+    def __len__(self) -> int:
+        return len(self.paulis)
+
+    def __getitem__(self, index) -> "SparsePauliOp":
+        if isinstance(index, (int, np.integer)):
+            index = [int(index)]
+        return SparsePauliOp(self.paulis[index], self.coeffs[index])
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def __repr__(self) -> str:
+        return f"SparsePauliOp({self.paulis.to_labels()}, coeffs={self.coeffs.tolist()})"
 
 
 class BitArray:

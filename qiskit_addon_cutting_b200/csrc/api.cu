@@ -49,6 +49,7 @@ int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, i
 size_t reduce_workspace_bytes(int64_t, int);
 int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const uint64_t*, const int64_t*,
                  const uint64_t*, int, const uint64_t*, int, const double*, double*, cudaStream_t);
+int launch_recombine(const double*, bool, const uint32_t*, const uint32_t*, const double*, int, double*, cudaStream_t);
 
 // Groups with at least this many terms are worth an NVRTC specialisation: below it the (shared)
 // load + transposition cost dominates and the run-time-mask kernel is within a few percent.
@@ -365,6 +366,15 @@ int qcut_quasi_launch(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_gr
   if (n_pubs < 0 || n_limbs_obs < 0 || n_limbs_qpd < 0) return set_error("qcut_quasi_launch: bad size"), QCUT_ERR_INVALID;
   return launch_quasi(d_pubs, n_pubs, d_groups, d_mask_limbs, d_dist_start, d_obs_bits, n_limbs_obs,
                       d_qpd_bits, n_limbs_qpd, d_weights, d_expvals, static_cast<cudaStream_t>(stream));
+}
+
+int qcut_recombine_launch(const double* d_term_expvals, int expvals_complex, const uint32_t* d_row_start,
+                          const uint32_t* d_term_index, const double* d_coeffs, int n_rows, double* d_out,
+                          void* stream) {
+  if (n_rows < 0 || (n_rows > 0 && (!d_row_start || !d_out)))
+    return set_error("qcut_recombine_launch: bad argument"), QCUT_ERR_INVALID;
+  return launch_recombine(d_term_expvals, expvals_complex != 0, d_row_start, d_term_index, d_coeffs, n_rows, d_out,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,

@@ -444,4 +444,73 @@ int launch_quasi(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_group_d
   return QCUT_OK;
 }
 
+// ---- term recombination: out[r] = sum_j coeff[j] * e[index[j]] (complex fp64, reference order) ----
+// One warp per observable: the lanes form 128 products at a time (coalesced coefficient loads, gathered
+// expectation values, four independent loads in flight per lane) and park them in shared memory; lane 0
+// then adds them in ascending j -- the reference's order and rounding (utils/observable_terms.py:66-79:
+// `rv = 0.0j; rv += coeff * term_expval`).  The sum is a dependent chain by definition, so a row runs at
+// DADD latency; rows run side by side on the other warps.  Complex product as NumPy's scalar multiply:
+// (ar*br - ai*bi, ar*bi + ai*br), no contraction.
+constexpr int kRecombineWarps = 4;
+constexpr int kRecombineChunk = 128;
+
+__global__ void __launch_bounds__(32 * kRecombineWarps)
+    recombine_kernel(const double* __restrict__ e, int e_complex, const uint32_t* __restrict__ row_start,
+                     const uint32_t* __restrict__ term_index, const double2* __restrict__ coeff, int n_rows,
+                     double2* __restrict__ out) {
+  __shared__ double2 products[kRecombineWarps][kRecombineChunk];
+  const int lane = threadIdx.x & 31;
+  double2* mine = products[threadIdx.x >> 5];
+  const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int n_warps = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
+  for (int r = warp; r < n_rows; r += n_warps) {
+    const uint32_t lo = row_start[r], hi = row_start[r + 1];
+    double re = 0.0, im = 0.0;
+    for (uint32_t base = lo; base < hi; base += kRecombineChunk) {
+      double2 c[4];
+      uint32_t t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = base + (uint32_t)(u * 32 + lane);
+        c[u] = j < hi ? coeff[j] : make_double2(0.0, 0.0);
+        t[u] = j < hi ? term_index[j] : 0u;
+      }
+      double er[4], ei[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool ok = base + (uint32_t)(u * 32 + lane) < hi;
+        er[u] = !ok ? 0.0 : e_complex ? e[2 * (size_t)t[u]] : e[t[u]];
+        ei[u] = (ok && e_complex) ? e[2 * (size_t)t[u] + 1] : 0.0;
+      }
+      __syncwarp();  // lane 0 is done with the previous chunk
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        mine[u * 32 + lane] = make_double2(__dsub_rn(__dmul_rn(c[u].x, er[u]), __dmul_rn(c[u].y, ei[u])),
+                                           __dadd_rn(__dmul_rn(c[u].x, ei[u]), __dmul_rn(c[u].y, er[u])));
+      __syncwarp();
+      if (lane == 0) {
+        const int n = (int)min((uint32_t)kRecombineChunk, hi - base);
+#pragma unroll 8
+        for (int k = 0; k < n; ++k) {
+          const double2 p = mine[k];
+          re = __dadd_rn(re, p.x);
+          im = __dadd_rn(im, p.y);
+        }
+      }
+    }
+    if (lane == 0) out[r] = make_double2(re, im);
+  }
+}
+
+int launch_recombine(const double* d_e, bool e_complex, const uint32_t* d_row_start, const uint32_t* d_term_index,
+                     const double* d_coeffs, int n_rows, double* d_out, cudaStream_t stream) {
+  if (n_rows <= 0) return QCUT_OK;
+  const int blocks = (int)std::min<int64_t>(((int64_t)n_rows + kRecombineWarps - 1) / kRecombineWarps, 148 * 16);
+  recombine_kernel<<<blocks, 32 * kRecombineWarps, 0, stream>>>(d_e, e_complex ? 1 : 0, d_row_start, d_term_index,
+                                               reinterpret_cast<const double2*>(d_coeffs), n_rows,
+                                               reinterpret_cast<double2*>(d_out));
+  QCUT_CUDA(cudaGetLastError());
+  return QCUT_OK;
+}
+
 }  // namespace qcut

@@ -222,3 +222,36 @@ SMALL_CASES = {
     "unpartitioned": case_unpartitioned,
     "pow2": case_pow2,
 }
+
+
+# ---- term recombination (reference utils/observable_terms.py) ------------------------------------------
+def terms_case(seed: int, complex_values: bool, n_qubits: int = 5, pool: int = 40, n_observables: int = 14):
+    """Seeded observables (SparsePauliOps with complex coefficients, zero coefficients, phased labels, bare
+    Paulis) and the expectation value of every unique term.  Returns (observables, {Pauli: value})."""
+    from qiskit_addon_cutting_b200.containers import Pauli, SparsePauliOp
+
+    rng = np.random.default_rng(seed)
+    labels = sorted({"".join(rng.choice(list("IXYZ"), size=n_qubits)) for _ in range(pool)})
+    observables = []
+    for k in range(n_observables):
+        if k % 5 == 4:
+            observables.append(Pauli(["", "-", "i", "-i"][int(rng.integers(4))] + labels[int(rng.integers(len(labels)))]))
+            continue
+        n_terms = int(rng.integers(1, 70 if k % 3 == 0 else 9))  # some rows longer than one warp pass
+        chosen = [labels[int(i)] for i in rng.integers(len(labels), size=n_terms)]  # repeats allowed
+        chosen = [["", "-", "i"][int(rng.integers(3))] + c for c in chosen]
+        coeffs = rng.normal(size=n_terms) + 1j * rng.normal(size=n_terms) * (rng.random(n_terms) < 0.5)
+        coeffs[rng.random(n_terms) < 0.15] = 0
+        observables.append(SparsePauliOp(chosen, coeffs))
+    values = {}
+    for lab in labels:
+        v = float(rng.uniform(-1, 1))
+        values[Pauli(lab)] = complex(v, float(rng.uniform(-1, 1))) if complex_values else v
+    return observables, values
+
+
+TERMS_CASES = {
+    "real": lambda: terms_case(1201, False),
+    "complex": lambda: terms_case(1202, True),
+    "single_qubit": lambda: terms_case(1203, False, n_qubits=1, pool=8, n_observables=6),
+}

@@ -141,6 +141,51 @@ def dump_case(name: str, ref: dict, results, coefficients, observables) -> dict:
     }
 
 
+def load_reference_terms():
+    """The reference's ``utils/observable_terms.py``, imported unmodified against the stand-ins."""
+    qi = sys.modules["qiskit.quantum_info"]
+    qi.SparsePauliOp = C.SparsePauliOp
+    spec = importlib.util.spec_from_file_location("_ref_observable_terms", REF / "utils" / "observable_terms.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def dump_observable(o) -> dict:
+    if isinstance(o, C.Pauli):
+        return {"pauli": o.to_label()}
+    return {"labels": o.paulis.to_labels(), "coeffs": [[float(c.real).hex(), float(c.imag).hex()] for c in o.coeffs]}
+
+
+def main_terms() -> None:
+    """Golden vectors for gather_unique_observable_terms / reconstruct_observable_expvals_from_terms."""
+    mod = load_reference_terms()
+    # the reference's own known answers (test/utils/test_observable_terms.py:61-91)
+    evs = mod.reconstruct_observable_expvals_from_terms(
+        [C.Pauli("XX"), C.SparsePauliOp(C.PauliList(["iXY", "ZZ", "XX"]))],
+        {C.Pauli("XX"): 7, C.Pauli("XY"): 11, C.Pauli("ZZ"): 13},
+    )
+    assert evs == [7, 20 + 11j], evs
+    assert mod.reconstruct_observable_expvals_from_terms([C.SparsePauliOp(["XX", "-XY"], [0, 1])], {C.Pauli("XY"): 3}) == [-3]
+    assert mod.reconstruct_observable_expvals_from_terms(C.PauliList(["iXY", "-ZZ"]), {C.Pauli("XY"): 7, C.Pauli("ZZ"): 11}) == [7j, -11]
+    assert mod.gather_unique_observable_terms([C.Pauli("-XX"), C.SparsePauliOp(C.PauliList(["iXY", "ZZ", "XX"]))]) == C.PauliList(["XX", "XY", "ZZ"])
+    cases = {}
+    for name, make in _cases.TERMS_CASES.items():
+        observables, values = make()
+        out = mod.reconstruct_observable_expvals_from_terms(observables, values)
+        unique = mod.gather_unique_observable_terms(observables)
+        cases[name] = {
+            "observables": [dump_observable(o) for o in observables],
+            "term_expvals": [[p.to_label(), float(np.real(v)).hex(), float(np.imag(v)).hex() if isinstance(v, complex) else None]
+                             for p, v in values.items()],
+            "unique_terms": unique.to_labels(),
+            "reference_expvals": [[float(np.real(v)).hex(), float(np.imag(v)).hex()] for v in out],
+        }
+        print(f"terms/{name:12s} expvals[:2] = {[complex(v) for v in out[:2]]}")
+    (HERE / "terms_cases.json").write_text(json.dumps(cases) + "\n")
+
+
 def main() -> None:
     ref = load_reference()
     recon = ref["reconstruct_expectation_values"]
@@ -224,4 +269,9 @@ def main() -> None:
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["terms"]:
+        load_reference()
+        main_terms()
+    else:
+        main()
+        main_terms()

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <mutex>
 #include <thread>
 
 #include "common.cuh"
@@ -238,6 +239,55 @@ size_t qcut_plan_source(const qcut_plan* plan, int kernel, char* buf, size_t buf
   return src.size() + 1;
 }
 
+}  // extern "C"
+
+namespace {
+// Descriptor buffers of schedules are recycled: a schedule lives for one reconstruction call, and
+// cudaFree of its (few MB) buffers was measured at up to 165 ms on a busy device -- half of an
+// end-to-end call.  Freed buffers wait here (a handful per device) for the next schedule.
+struct CachedBuffer { void* ptr; size_t bytes; int device; };
+std::mutex g_cache_mutex;
+std::vector<CachedBuffer> g_cache;
+constexpr size_t kCacheEntries = 8;
+
+cudaError_t cached_alloc(void** ptr, size_t bytes, size_t* capacity, int device) {
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    int best = -1;
+    for (int i = 0; i < (int)g_cache.size(); ++i) {
+      const CachedBuffer& c = g_cache[(size_t)i];
+      if (c.device == device && c.bytes >= bytes && c.bytes <= 4 * bytes + (1u << 20) &&
+          (best < 0 || c.bytes < g_cache[(size_t)best].bytes))
+        best = i;
+    }
+    if (best >= 0) {
+      *ptr = g_cache[(size_t)best].ptr;
+      *capacity = g_cache[(size_t)best].bytes;
+      g_cache.erase(g_cache.begin() + best);
+      return cudaSuccess;
+    }
+  }
+  *capacity = bytes;
+  return cudaMalloc(ptr, bytes);
+}
+
+void cached_release(void* ptr, size_t bytes, int device) {
+  if (!ptr) return;
+  void* evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    g_cache.push_back(CachedBuffer{ptr, bytes, device});
+    if (g_cache.size() > kCacheEntries) {
+      evict = g_cache.front().ptr;
+      g_cache.erase(g_cache.begin());
+    }
+  }
+  if (evict) cudaFree(evict);
+}
+}  // namespace
+
+extern "C" {
+
 int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int64_t n_pubs,
                          qcut_schedule** out_schedule) {
   if (!out_schedule) return set_error("qcut_schedule_create: out_schedule is NULL"), QCUT_ERR_INVALID;
@@ -280,13 +330,16 @@ int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int
     qcut_schedule_destroy(sch);
     return rc;
   };
-  cudaError_t err = cudaMalloc(&sch->d_pubs, sizeof(qcut_pub_desc) * (size_t)std::max<int64_t>(n_pubs, 1));
+  cudaError_t err = cudaGetDevice(&sch->device);
+  if (err != cudaSuccess) return fail(err, "cudaGetDevice");
+  err = cached_alloc(reinterpret_cast<void**>(&sch->d_pubs), sizeof(qcut_pub_desc) * (size_t)std::max<int64_t>(n_pubs, 1),
+                     &sch->pubs_capacity, sch->device);
   if (err != cudaSuccess) return fail(err, "cudaMalloc(pubs)");
   if (n_pubs) {
     err = cudaMemcpy(sch->d_pubs, h_pubs, sizeof(qcut_pub_desc) * (size_t)n_pubs, cudaMemcpyHostToDevice);
     if (err != cudaSuccess) return fail(err, "cudaMemcpy(pubs)");
   }
-  err = cudaMalloc(&sch->d_tiles, sizeof(TileEntry) * tiles.size());
+  err = cached_alloc(reinterpret_cast<void**>(&sch->d_tiles), sizeof(TileEntry) * tiles.size(), &sch->tiles_capacity, sch->device);
   if (err != cudaSuccess) return fail(err, "cudaMalloc(tiles)");
   if (sch->n_tiles) {
     err = cudaMemcpy(sch->d_tiles, tiles.data(), sizeof(TileEntry) * (size_t)sch->n_tiles, cudaMemcpyHostToDevice);
@@ -298,8 +351,16 @@ int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int
 
 void qcut_schedule_destroy(qcut_schedule* schedule) {
   if (!schedule) return;
-  if (schedule->d_pubs) cudaFree(schedule->d_pubs);
-  if (schedule->d_tiles) cudaFree(schedule->d_tiles);
+  // Like the cudaFree it replaces, wait for launches that may still read the descriptors before the
+  // buffers can be handed to the next schedule (idle device: microseconds).
+  int current = -1;
+  if (cudaGetDevice(&current) == cudaSuccess) {
+    if (current != schedule->device) cudaSetDevice(schedule->device);
+    cudaDeviceSynchronize();
+    if (current != schedule->device) cudaSetDevice(current);
+  }
+  cached_release(schedule->d_pubs, schedule->pubs_capacity, schedule->device);
+  cached_release(schedule->d_tiles, schedule->tiles_capacity, schedule->device);
   delete schedule;
 }
 

@@ -75,5 +75,7 @@ struct qcut_schedule {
   int64_t n_tiles = 0;
   qcut_pub_desc* d_pubs = nullptr;
   qcut::TileEntry* d_tiles = nullptr;      // sorted by kernel id, PUB order within a kernel
+  size_t pubs_capacity = 0, tiles_capacity = 0;  // bytes behind d_pubs / d_tiles (buffers come from a cache)
+  int device = 0;
   std::vector<int64_t> kernel_tile_begin;  // n_kernels + 1 offsets into d_tiles
 };

@@ -12,8 +12,10 @@ Terminology follows the reference: a *PUB* is the result of one subexperiment
 from __future__ import annotations
 
 import ctypes as C
+import os
 import queue
 import threading
+import time
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -458,7 +460,7 @@ def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_thread
     )
 
 
-_STAGING_BYTES = 256 << 20  # pinned staging ring for the end-to-end path, independent of the problem size
+_STAGING_BYTES = int(os.environ.get("QCUT_STAGING_MB", "256")) << 20  # pinned staging ring of the end-to-end path, independent of the problem size
 _BLOCK_PUBS = 2048  # PUBs in the first staging block of a label (~1 ms of attribute walk); later blocks grow 4x
 
 
@@ -478,6 +480,7 @@ class _BlockStager:
         self.blocks: list[torch.Tensor] = []
         self.base = 0
         self.error: BaseException | None = None
+        self.block_seconds: list[tuple[int, float, float]] = []  # (bytes, start, end) of every staged block
         self.queue: queue.SimpleQueue = queue.SimpleQueue()
         self.thread = threading.Thread(target=self._run, name="qcut-stage", daemon=True)
         self.thread.start()
@@ -504,11 +507,13 @@ class _BlockStager:
                 if self.error is not None:
                     continue  # drain
                 src, nbytes, dst, d_ptr = item
+                t0 = time.perf_counter()
                 check(
                     lib.qcut_stage_h2d(_lib.np_ptr(src), _lib.np_ptr(nbytes), _lib.np_ptr(dst), len(src),
                                        self.pinned.data_ptr(), self.pinned.numel(), d_ptr, 0, self.stream),
                     "qcut_stage_h2d",
                 )
+                self.block_seconds.append((int(nbytes.sum()), t0, time.perf_counter()))
         except BaseException as ex:  # noqa: BLE001 - re-raised on the caller's thread by finish()
             self.error = ex
 
@@ -532,6 +537,7 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
     ring and queue one H2D copy per run: attribute walk, host gather and PCIe transfer all overlap.
     """
     _lib.require_device()
+    t_start = time.perf_counter()
     stager = _BlockStager()
     try:
         tables, _ = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, sink=stager,
@@ -540,10 +546,20 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
         stager.finish(raise_errors=False)
         raise
     # plan lookup / schedule upload proceed while the last blocks are still in flight
+    t_walked = time.perf_counter()
     try:
         batch = DeviceBatch(tables, stager, flags=flags)
     finally:
+        t_batch = time.perf_counter()
         stager.finish(raise_errors=False)
     if stager.error is not None:
         raise stager.error
+    global last_stage_trace
+    last_stage_trace = {
+        "walk_s": t_walked - t_start, "tables_s": t_batch - t_walked, "wait_s": time.perf_counter() - t_batch,
+        "blocks": [(b, s - t_start, e - t_start) for b, s, e in stager.block_seconds],
+    }
     return batch
+
+
+last_stage_trace: dict = {}  # timing of the most recent stage_v2 call (diagnostics only)

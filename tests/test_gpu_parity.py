@@ -166,3 +166,16 @@ def test_reduction_for_any_number_of_subsystems(lib, n_labels, C):
         assert _hex(out) == _hex(want)
     else:
         assert np.max(np.abs(out - want)) <= 1e-13 * 27.0
+
+
+@pytest.mark.parametrize("name", ["molecular", "odd_widths", "wire"])
+def test_block_staging_many_blocks(lib, monkeypatch, name):
+    """Tiny staging blocks (every label cut into several device allocations): same tallies, same result."""
+    results, coefficients, observables = _cases.SMALL_CASES[name]()
+    monkeypatch.setattr(engine, "_BLOCK_PUBS", 2)
+    batch, got, want = _device_tallies(results, coefficients, observables)
+    assert len(batch.data.blocks) > len(observables if isinstance(observables, dict) else [0])
+    assert np.array_equal(got, want)
+    out = reconstruct_expectation_values(results, coefficients, observables)
+    monkeypatch.undo()
+    assert _hex(out) == _hex(reconstruct_expectation_values(results, coefficients, observables))

@@ -482,8 +482,16 @@ class _BlockStager:
         self.error: BaseException | None = None
         self.block_seconds: list[tuple[int, float, float]] = []  # (bytes, start, end) of every staged block
         self.queue: queue.SimpleQueue = queue.SimpleQueue()
-        self.thread = threading.Thread(target=self._run, name="qcut-stage", daemon=True)
-        self.thread.start()
+        # two feeders, each with half of the ring: the pipeline fill of one block (gather before the first
+        # copy) overlaps the drain of the previous one
+        half = (self.pinned.numel() // 2) & ~4095
+        self.threads = [
+            threading.Thread(target=self._run, args=(self.pinned.data_ptr() + i * half, half), name=f"qcut-stage-{i}",
+                             daemon=True)
+            for i in range(2)
+        ]
+        for t in self.threads:
+            t.start()
 
     def __call__(self, src: np.ndarray, nbytes: np.ndarray, dst: np.ndarray, block_bytes: int) -> int:
         block = torch.empty(block_bytes + _lib.DATA_SLACK, dtype=torch.uint8, device="cuda")
@@ -496,7 +504,7 @@ class _BlockStager:
         self.base = min(addresses) if addresses else 0
         return [a - self.base for a in addresses]
 
-    def _run(self) -> None:
+    def _run(self, ring_ptr: int, ring_bytes: int) -> None:
         try:
             torch.cuda.set_device(self.device)  # qcut_stage_h2d copies to the calling thread's device
             lib = _lib.load()
@@ -510,7 +518,7 @@ class _BlockStager:
                 t0 = time.perf_counter()
                 check(
                     lib.qcut_stage_h2d(_lib.np_ptr(src), _lib.np_ptr(nbytes), _lib.np_ptr(dst), len(src),
-                                       self.pinned.data_ptr(), self.pinned.numel(), d_ptr, 0, self.stream),
+                                       ring_ptr, ring_bytes, d_ptr, 8, self.stream),
                     "qcut_stage_h2d",
                 )
                 self.block_seconds.append((int(nbytes.sum()), t0, time.perf_counter()))
@@ -519,8 +527,10 @@ class _BlockStager:
 
     def finish(self, *, raise_errors: bool = True) -> None:
         """Wait until every queued block is in HBM (``qcut_stage_h2d`` returns after its last copy)."""
-        self.queue.put(None)
-        self.thread.join()
+        for _ in self.threads:
+            self.queue.put(None)
+        for t in self.threads:
+            t.join()
         if raise_errors and self.error is not None:
             raise self.error
 

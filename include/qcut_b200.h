@@ -188,7 +188,7 @@ int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const ui
 
 /* Pipelined version of the above for the end-to-end path: worker threads gather runs of arrays into
  * slots of a (small) pinned buffer and queue one H2D copy per slot on `stream`, so the host-side
- * gather overlaps the PCIe transfer and only pinned_bytes (e.g. 256 MiB) of pinned memory is needed
+ * gather overlaps the PCIe transfer and only pinned_bytes (e.g. 64 MiB) of pinned memory is needed
  * whatever the problem size.  Arrays must be sorted by h_dst_offset; d_dst + h_dst_offset[i] receives
  * array i.  Returns when every byte has left host memory (the copies may still be in flight). */
 int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,

@@ -22,6 +22,8 @@ from pathlib import Path
 
 import numpy as np
 
+os.environ.setdefault("QCUT_CACHE_DIR", "/tmp/qcut_b200_cache")  # compiled-kernel cache of harness runs: not under $HOME
+
 ROOT = Path(__file__).resolve().parent
 for _p in (ROOT, ROOT / "tests"):
     if str(_p) not in sys.path:

@@ -104,7 +104,10 @@ int qcut_device_count(void);
  *   specialised by NVRTC for the groups' masks: one kernel per group for the QCUT_MAX_JIT_KERNELS
  *   groups with the most terms (>= 12), multi-group kernels (one __noinline__ function per group)
  *   for the other groups with rows of <= 8 bytes; what is left uses kernel 0/1.
- * flags: QCUT_PLAN_NO_JIT disables NVRTC specialisation, QCUT_PLAN_GENERIC_ONLY forces kernel 0. */
+ * flags: QCUT_PLAN_NO_JIT disables NVRTC specialisation, QCUT_PLAN_GENERIC_ONLY forces kernel 0.
+ * Compiled kernels are cached on disk, keyed by a hash of the generated source, the NVRTC version and
+ * the options: $QCUT_CACHE_DIR, default $XDG_CACHE_HOME/qcut_b200 or ~/.cache/qcut_b200;
+ * QCUT_CACHE_DIR="" disables the cache. */
 #define QCUT_PLAN_NO_JIT 1u
 #define QCUT_PLAN_GENERIC_ONLY 2u
 #define QCUT_PLAN_STAGED 4u /* specialised kernels prefetch each step through shared memory with bulk async copies (UBLKCP + mbarrier) instead of loading straight from HBM; measured slower on B200 for this ALU-issue-bound kernel, kept for experiments */

@@ -10,8 +10,13 @@
 
 #include <algorithm>
 #include <atomic>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <sstream>
 #include <thread>
 
@@ -333,18 +338,88 @@ static std::string nvrtc_log(nvrtcProgram prog) {
   return log;
 }
 
-// NVRTC: CUDA C++ -> sm_100a cubin.  Needs no GPU, so the CPU test-suite compiles plans too.
-// Thread safe (no use of the thread-local error string): the message is returned in *error.
+// ---- on-disk cache of compiled kernels ---------------------------------------------------------
+// A cubin is a pure function of (generated source, NVRTC version, options), and a plan of 332 groups
+// costs ~15 s of NVRTC per process.  Cubins are kept under $QCUT_CACHE_DIR (default
+// $XDG_CACHE_HOME/qcut_b200 or ~/.cache/qcut_b200; QCUT_CACHE_DIR="" switches the cache off), named by a
+// 128-bit hash of everything they depend on, written to a temporary name and renamed (atomic on POSIX,
+// so concurrent ranks never see half a file).  A file that is not an ELF image is ignored and replaced.
+static const char* const kNvrtcOptions[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+
+static std::string cache_dir() {
+  if (const char* dir = std::getenv("QCUT_CACHE_DIR")) return std::string(dir);
+  if (const char* xdg = std::getenv("XDG_CACHE_HOME"))
+    if (*xdg) return std::string(xdg) + "/qcut_b200";
+  if (const char* home = std::getenv("HOME"))
+    if (*home) return std::string(home) + "/.cache/qcut_b200";
+  return std::string();
+}
+
+static std::string cache_key(const std::string& source) {
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  std::string text = "nvrtc " + std::to_string(major) + "." + std::to_string(minor);
+  for (const char* o : kNvrtcOptions) text += std::string(" ") + o;
+  text += "\n" + source;
+  uint64_t h1 = 0xcbf29ce484222325ull, h2 = 0x9ae16a3b2f90404full;  // two FNV-1a streams, different offsets / primes
+  for (unsigned char c : text) {
+    h1 = (h1 ^ c) * 0x100000001b3ull;
+    h2 = (h2 ^ c) * 0x00000100000001b5ull + 0x9e3779b97f4a7c15ull;
+  }
+  char name[40];
+  std::snprintf(name, sizeof name, "%016llx%016llx", (unsigned long long)h1, (unsigned long long)h2);
+  return std::string(name);
+}
+
+static bool cache_load(const std::string& path, std::vector<char>* cubin) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::vector<char> data;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) data.insert(data.end(), buf, buf + n);
+  std::fclose(f);
+  if (data.size() < 64 || std::memcmp(data.data(), "\177ELF", 4) != 0) return false;
+  cubin->swap(data);
+  return true;
+}
+
+static void cache_store(const std::string& dir, const std::string& path, const std::vector<char>& cubin) {
+  ::mkdir(dir.c_str(), 0700);  // one level; a missing parent simply leaves the cache off
+  const std::string tmp = path + "." + std::to_string((long long)::getpid()) + "." +
+                          std::to_string((unsigned long long)std::hash<std::thread::id>()(std::this_thread::get_id())) + ".tmp";
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  if (std::fclose(f) != 0 || !ok || std::rename(tmp.c_str(), path.c_str()) != 0) std::remove(tmp.c_str());
+}
+
+static int compile_with_nvrtc(const std::string& source, std::vector<char>* cubin, std::string* log, std::string* error);
+
+// Generated source -> sm_100a cubin, through the on-disk cache.  Needs no GPU, so the CPU test-suite
+// compiles plans too.  Thread safe (no use of the thread-local error string): the message is returned in *error.
 int compile_sliced_source(const std::string& source, std::vector<char>* cubin, std::string* log,
                           std::string* error) {
+  const std::string dir = cache_dir();
+  const std::string path = dir.empty() ? std::string() : dir + "/" + cache_key(source) + ".cubin";
+  if (!path.empty() && cache_load(path, cubin)) {
+    if (log) *log = "(cubin from " + path + ")";
+    return QCUT_OK;
+  }
+  const int rc = compile_with_nvrtc(source, cubin, log, error);
+  if (rc == QCUT_OK && !path.empty()) cache_store(dir, path, *cubin);
+  return rc;
+}
+
+static int compile_with_nvrtc(const std::string& source, std::vector<char>* cubin, std::string* log,
+                              std::string* error) {
   nvrtcProgram prog = nullptr;
   nvrtcResult rc = nvrtcCreateProgram(&prog, source.c_str(), "qcut_tally_sliced.cu", 0, nullptr, nullptr);
   if (rc != NVRTC_SUCCESS) {
     *error = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(rc);
     return QCUT_ERR_JIT;
   }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
-  rc = nvrtcCompileProgram(prog, 4, opts);
+  rc = nvrtcCompileProgram(prog, (int)(sizeof kNvrtcOptions / sizeof kNvrtcOptions[0]), kNvrtcOptions);
   if (log) *log = nvrtc_log(prog);
   if (rc != NVRTC_SUCCESS) {
     *error = std::string("nvrtcCompileProgram: ") + nvrtcGetErrorString(rc) + "\n" + nvrtc_log(prog);
@@ -413,6 +488,16 @@ int jit_build(qcut_plan* plan, bool load) {
   if (!load) return QCUT_OK;  // compile check only (no device needed)
   for (JitKernel& jk : plan->jit) {
     cudaError_t err = cudaLibraryLoadData(&jk.library, jk.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (err != cudaSuccess && jk.log.rfind("(cubin from ", 0) == 0) {
+      // a cached image the driver rejects (e.g. damaged file): compile it again, which also replaces the file
+      cudaGetLastError();
+      std::string error;
+      const std::string path = jk.log.substr(12, jk.log.size() - 13);
+      std::remove(path.c_str());
+      const int rc = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &error);
+      if (rc != QCUT_OK) return set_error(error), rc;
+      err = cudaLibraryLoadData(&jk.library, jk.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    }
     if (err == cudaSuccess) err = cudaLibraryGetKernel(&jk.kernel, jk.library, "qcut_tally_sliced");
     if (err != cudaSuccess) return cuda_fail(err, "cudaLibraryLoadData(qcut_tally_sliced)");
     if (jk.variants.empty() && jk.nb_obs > 8) {

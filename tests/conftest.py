@@ -1,9 +1,12 @@
+import os
 import sys
 from pathlib import Path
 
 import pytest
 
 ROOT = Path(__file__).resolve().parents[1]
+# compiled-kernel cache of the test runs: not under $HOME
+os.environ.setdefault("QCUT_CACHE_DIR", "/tmp/qcut_b200_cache")
 for p in (ROOT, ROOT / "tests"):
     if str(p) not in sys.path:
         sys.path.insert(0, str(p))

@@ -78,3 +78,38 @@ def test_install_patches_the_reference_when_importable(monkeypatch):
     assert install() is True
     assert pkg.reconstruct_expectation_values is reconstruct_expectation_values
     assert sub.reconstruct_expectation_values is reconstruct_expectation_values
+
+
+def test_compiled_kernels_are_cached_on_disk(lib, tmp_path, monkeypatch):
+    """Cubins are stored under $QCUT_CACHE_DIR keyed by the source; damaged files are replaced; "" disables."""
+    import time
+
+    from qiskit_addon_cutting_b200 import _lib as L
+
+    groups = np.array([(14, 2, 0, 0)], dtype=L.GROUP_DTYPE)
+    masks = np.random.default_rng(5).integers(0, 256, size=28, dtype=np.uint8)
+    cache = tmp_path / "cubins"
+    monkeypatch.setenv("QCUT_CACHE_DIR", str(cache))
+    t0 = time.perf_counter()
+    n, size = L.plan_compile_check(groups, masks)
+    cold = time.perf_counter() - t0
+    files = sorted(cache.glob("*.cubin"))
+    assert n == 1 and len(files) == 1 and files[0].stat().st_size == size and files[0].read_bytes()[:4] == b"\x7fELF"
+    t0 = time.perf_counter()
+    assert L.plan_compile_check(groups, masks) == (n, size)
+    assert time.perf_counter() - t0 < cold / 3  # no NVRTC run
+    assert not list(cache.glob("*.tmp"))
+    # a different mask set is a different kernel
+    masks2 = masks.copy()
+    masks2[0] ^= 1
+    L.plan_compile_check(groups, masks2)
+    assert len(list(cache.glob("*.cubin"))) == 2
+    # a damaged file is not trusted
+    files[0].write_bytes(b"garbage")
+    assert L.plan_compile_check(groups, masks) == (n, size)
+    assert files[0].read_bytes()[:4] == b"\x7fELF"
+    # switched off
+    monkeypatch.setenv("QCUT_CACHE_DIR", "")
+    before = len(list(cache.glob("*")))
+    assert L.plan_compile_check(groups, masks) == (n, size)
+    assert len(list(cache.glob("*"))) == before

@@ -460,10 +460,21 @@ def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_thread
     )
 
 
-# Pinned staging ring of the end-to-end path, independent of the problem size.  64 MiB measured best: same rate as
-# 256 MiB with one rank per host (327 ms per cfg4 call), 23 % faster with two (415 vs 540 ms) because the ring
-# stays closer to the last-level cache the DMA engine reads from; 32 / 16 MiB slots are too small for PCIe.
-_STAGING_BYTES = int(os.environ.get("QCUT_STAGING_MB", "64")) << 20
+# Pinned staging ring of the end-to-end path, independent of the problem size.  Measured on cfg4 (14.3 GB per
+# call, PCIe ceiling of the box 55 GB/s): one rank per host 308 ms with 128 MiB, 326 ms with 64 or 256 MiB,
+# 352 ms with 32 MiB (pieces too small for PCIe); two ranks on one 24-core host 415 ms with 64 MiB, 540 ms
+# with 256 MiB (the host's memory bandwidth is the limit there, and a small ring stays closer to the
+# last-level cache the DMA engine reads from).  Hence: 128 MiB alone on a host, 64 MiB with local peers.
+def _default_staging_mb() -> int:
+    try:
+        peers = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    except ValueError:
+        peers = 1
+    return 128 if peers <= 1 else 64
+
+
+_STAGING_BYTES = int(os.environ.get("QCUT_STAGING_MB", "0") or 0) << 20 or _default_staging_mb() << 20
+_STAGING_THREADS = int(os.environ.get("QCUT_STAGING_THREADS", "8"))  # gather threads per feeder (two feeders)
 _BLOCK_PUBS = 2048  # PUBs in the first staging block of a label (~1 ms of attribute walk); later blocks grow 4x
 
 
@@ -521,7 +532,7 @@ class _BlockStager:
                 t0 = time.perf_counter()
                 check(
                     lib.qcut_stage_h2d(_lib.np_ptr(src), _lib.np_ptr(nbytes), _lib.np_ptr(dst), len(src),
-                                       ring_ptr, ring_bytes, d_ptr, 8, self.stream),
+                                       ring_ptr, ring_bytes, d_ptr, _STAGING_THREADS, self.stream),
                     "qcut_stage_h2d",
                 )
                 self.block_seconds.append((int(nbytes.sum()), t0, time.perf_counter()))

@@ -3,8 +3,9 @@
 set -u
 OUT=gpurun_out; mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1 || { tail -20 $OUT/build.log; exit 1; }
-for mb in ${SIZES:-256 64}; do
-QCUT_STAGING_MB=$mb python - <<'PY'
+for cfg in ${SIZES:-256 64}; do
+mb=${cfg%%:*}; th=${cfg##*:}; [ "$th" = "$cfg" ] && th=8
+QCUT_STAGING_MB=$mb QCUT_STAGING_THREADS=$th python - <<'PY'
 import os, time, numpy as np, torch, sys
 sys.path.insert(0, ".")
 import workloads as W
@@ -19,7 +20,7 @@ pairs = W.coefficient_pairs(coeffs)
 keep_resident = os.environ.get("KEEP_RESIDENT", "1") == "1"
 if not keep_resident:
     del data
-print(f"ring {os.environ['QCUT_STAGING_MB']} MiB, resident copy kept: {keep_resident}")
+print(f"ring {os.environ['QCUT_STAGING_MB']} MiB, {os.environ['QCUT_STAGING_THREADS']} gather threads x 2 feeders, resident copy kept: {keep_resident}")
 import gc
 gclog = []
 def _cb(phase, info):

@@ -193,7 +193,8 @@ int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const ui
  * slots of a (small) pinned buffer and queue one H2D copy per slot on `stream`, so the host-side
  * gather overlaps the PCIe transfer and only pinned_bytes (e.g. 64 MiB) of pinned memory is needed
  * whatever the problem size.  Arrays must be sorted by h_dst_offset; d_dst + h_dst_offset[i] receives
- * array i.  Returns when every byte has left host memory (the copies may still be in flight). */
+ * array i.  Returns when every byte has left host memory (the copies may still be in flight).
+ * Rings of >= 64 MiB are written with non-temporal stores (QCUT_STAGING_NT=0/1 overrides). */
 int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint64_t* h_dst_offset,
                    int64_t n_arrays, void* h_pinned, size_t pinned_bytes, uint8_t* d_dst, int n_threads,
                    void* stream);

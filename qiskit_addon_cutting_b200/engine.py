@@ -461,16 +461,18 @@ def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_thread
 
 
 # Pinned staging ring of the end-to-end path, independent of the problem size.  Measured on cfg4 (14.3 GB per
-# call, PCIe ceiling of the box 55 GB/s): one rank per host 308 ms with 128 MiB, 326 ms with 64 or 256 MiB,
-# 352 ms with 32 MiB (pieces too small for PCIe); two ranks on one 24-core host 415 ms with 64 MiB, 540 ms
-# with 256 MiB (the host's memory bandwidth is the limit there, and a small ring stays closer to the
-# last-level cache the DMA engine reads from).  Hence: 128 MiB alone on a host, 64 MiB with local peers.
+# call, PCIe ceiling of the box 55 GB/s).  One rank per host: 292 ms with 256 MiB written with streaming stores
+# (qcut_stage_h2d does that for rings >= 64 MiB per call), 308 ms with 128 MiB / 326 ms with 64 or 256 MiB and
+# ordinary stores, 352 ms with 32 MiB (pieces too small for PCIe).  Two ranks on one 24-core host: the host's
+# memory bandwidth is the limit, 415 ms with a 64 MiB ring that stays close to the last-level cache the DMA
+# engine reads from, 460-473 ms with streaming stores, 540 ms with 256 MiB and ordinary stores.
+# Hence: 256 MiB alone on a host, 64 MiB with local peers.
 def _default_staging_mb() -> int:
     try:
         peers = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
     except ValueError:
         peers = 1
-    return 128 if peers <= 1 else 64
+    return 256 if peers <= 1 else 64
 
 
 _STAGING_BYTES = int(os.environ.get("QCUT_STAGING_MB", "0") or 0) << 20 or _default_staging_mb() << 20

@@ -4,8 +4,9 @@ set -u
 OUT=gpurun_out; mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1 || { tail -20 $OUT/build.log; exit 1; }
 for cfg in ${SIZES:-256 64}; do
-mb=${cfg%%:*}; th=${cfg##*:}; [ "$th" = "$cfg" ] && th=8
-QCUT_STAGING_MB=$mb QCUT_STAGING_THREADS=$th python - <<'PY'
+IFS=: read mb th nt <<< "$cfg"; th=${th:-8}; nt=${nt:-0}
+echo "== ring $mb MiB threads $th streaming-stores $nt"
+QCUT_STAGING_MB=$mb QCUT_STAGING_THREADS=$th QCUT_STAGING_NT=$nt python - <<'PY'
 import os, time, numpy as np, torch, sys
 sys.path.insert(0, ".")
 import workloads as W

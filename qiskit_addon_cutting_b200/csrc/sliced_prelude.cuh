@@ -256,9 +256,8 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
       const bool valid = FULL || (g * 32 + lane) * 16 < n;
 #pragma unroll
       for (int c = 0; c < NB; ++c) {
-        // tail steps: clamp the address instead of predicating the load (predicated loads issue one
-        // at a time); whatever an out-of-range lane reads is zeroed by qcut_mask_tail
-        const qcut_u4 v = src.obs16_shared_sectors(valid ? (g * 32 + lane) * 16 * NB + c * 16 : 0);
+        qcut_u4 v = {0u, 0u, 0u, 0u};
+        if (valid) v = src.obs16_shared_sectors((g * 32 + lane) * 16 * NB + c * 16);
         w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
       }
       w[4 * NB] = 0;
@@ -275,7 +274,8 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
   } else {
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
-      const qcut_u4 v = src.obs16((FULL || (k * 32 + lane) * G::SPC < n) ? lane * 16 + k * 512 : 0);
+      qcut_u4 v = {0u, 0u, 0u, 0u};
+      if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
       if constexpr (NB == 8) {
         a[0][2 * k] = v.x; a[1][2 * k] = v.y;
         a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
@@ -297,13 +297,15 @@ QCUT_DEV void qcut_qpd_loads(const Src src, int n, int lane, uint32_t* qraw) {
     // group g: the 16 qpd bytes of shots 16*(32g+lane) .. +15 -> words 4g .. 4g+3 (rows 16g+4w .. +3)
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      const qcut_u4 v = src.qpd16((FULL || (g * 32 + lane) * 16 < n) ? (g * 32 + lane) * 16 : 0);
+      qcut_u4 v = {0u, 0u, 0u, 0u};
+      if (FULL || (g * 32 + lane) * 16 < n) v = src.qpd16((g * 32 + lane) * 16);
       qraw[4 * g] = v.x; qraw[4 * g + 1] = v.y; qraw[4 * g + 2] = v.z; qraw[4 * g + 3] = v.w;
     }
   } else if constexpr (NB == 1) {
 #pragma unroll
     for (int k = 0; k < G::CHUNKS; ++k) {
-      const qcut_u4 v = src.qpd16((FULL || (k * 32 + lane) * G::SPC < n) ? lane * 16 + k * 512 : 0);
+      qcut_u4 v = {0u, 0u, 0u, 0u};
+      if (FULL || (k * 32 + lane) * G::SPC < n) v = src.qpd16(lane * 16 + k * 512);
       qraw[4 * k] = v.x; qraw[4 * k + 1] = v.y; qraw[4 * k + 2] = v.z; qraw[4 * k + 3] = v.w;
     }
   } else {
@@ -313,15 +315,20 @@ QCUT_DEV void qcut_qpd_loads(const Src src, int n, int lane, uint32_t* qraw) {
       const int idx = k * 32 + lane;
       if constexpr (NB == 8) {
         if (k & 1) continue;  // chunks k, k+1 -> rows 2k .. 2k+3
-        uint32_t w = src.qpd2((FULL || idx * 2 < n) ? ql + k * 64 : 0);
-        w |= src.qpd2((FULL || (idx + 32) * 2 < n) ? ql + (k + 1) * 64 : 0) << 16;
+        uint32_t w = 0;
+        if (FULL || idx * 2 < n) w = src.qpd2(ql + k * 64);
+        if (FULL || (idx + 32) * 2 < n) w |= src.qpd2(ql + (k + 1) * 64) << 16;
         qraw[k / 2] = w;
       } else if constexpr (NB == 4) {
-        qraw[k] = src.qpd4((FULL || idx * 4 < n) ? ql + k * 128 : 0);
+        uint32_t w = 0;
+        if (FULL || idx * 4 < n) w = src.qpd4(ql + k * 128);
+        qraw[k] = w;
       } else {  // NB == 2
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          qraw[2 * k + h] = src.qpd4((FULL || idx * 8 + 4 * h < n) ? ql + k * 256 + 4 * h : 0);
+          uint32_t w = 0;
+          if (FULL || idx * 8 + 4 * h < n) w = src.qpd4(ql + k * 256 + 4 * h);
+          qraw[2 * k + h] = w;
         }
       }
     }

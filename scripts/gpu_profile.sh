@@ -12,6 +12,8 @@ ncu --set full --clock-control none --import-source on -k regex:qcut_tally_slice
 echo "ncu exit $?"
 timeout 900 python bench.py > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench exit $?"; cat $OUT/bench_default.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2>&1; cut -c1-400 $OUT/bench_reference.json
-for wl in cfg3_wide_dense cfg3_wide_local cfg5_molecular cfg2_wire cfg1_tutorial; do
+for wl in cfg3_wide_dense cfg3_wide_local cfg5_molecular cfg2_wire cfg1_tutorial cfg4u_heavy_hex_unpartitioned; do
   timeout 600 python bench.py --workload $wl --steps 20 --warmup 3 --no-e2e --cpu-seconds 3 > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; echo "bench $wl exit $?"
 done
+bash scripts/gpu_terms.sh > $OUT/terms.log 2>&1; tail -3 $OUT/terms.log
+bash scripts/gpu_pcie.sh > $OUT/pcie.log 2>&1; cat $OUT/pcie.log

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "qcut_b200.h"
@@ -68,6 +69,13 @@ struct qcut_plan {
   uint32_t* d_mask_words = nullptr;        // little-endian words assembled from the byte rows
   std::vector<qcut::JitKernel> jit;        // kernel id = KERNEL_JIT0 + index
   int n_kernels() const { return (int)qcut::KERNEL_JIT0 + (int)jit.size(); }
+  // Side streams of qcut_tally_launch (created on first use, used under `side_mutex`): the K1 kernels of one
+  // launch write disjoint tallies, so they are spread over streams and the ramp of one overlaps the tail of another.
+  static constexpr int kSideStreams = 3;
+  mutable std::mutex side_mutex;
+  mutable cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
+  mutable cudaEvent_t fork_event = nullptr;
+  mutable cudaEvent_t join_event[kSideStreams] = {nullptr, nullptr, nullptr};
 };
 
 struct qcut_schedule {
@@ -78,4 +86,5 @@ struct qcut_schedule {
   size_t pubs_capacity = 0, tiles_capacity = 0;  // bytes behind d_pubs / d_tiles (buffers come from a cache)
   int device = 0;
   std::vector<int64_t> kernel_tile_begin;  // n_kernels + 1 offsets into d_tiles
+  std::vector<int64_t> kernel_bytes;       // shot bytes each kernel reads (decides whether launches overlap)
 };

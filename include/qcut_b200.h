@@ -122,7 +122,9 @@ size_t qcut_plan_source(const qcut_plan* plan, int kernel, char* buf, size_t buf
 
 /* ---- schedule -----------------------------------------------------------------------------------
  * Copies the PUB table to HBM and cuts every PUB into tiles of QCUT_TILE_SHOTS consecutive shots,
- * listed per kernel so that each K1 kernel streams only its own tiles. */
+ * listed per kernel so that each K1 kernel streams only its own tiles.  The two descriptor buffers
+ * come from a small per-process cache (destroy waits for the device, then parks them for the next
+ * schedule: cudaFree per call was measured at up to 165 ms). */
 int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int64_t n_pubs,
                          qcut_schedule** out_schedule);
 void qcut_schedule_destroy(qcut_schedule* schedule);
@@ -131,7 +133,12 @@ const qcut_pub_desc* qcut_schedule_device_pubs(const qcut_schedule* schedule);
 
 /* ---- K1: parity tallies (reference cutting_reconstruction.py:152-161 + :196-222) -------------
  * Zeroes d_tallies[0 .. n_tallies) and accumulates the exact sign tallies of every PUB of the
- * schedule into it.  Returns the number of kernels launched in *n_launches if not NULL. */
+ * schedule into it.  Returns the number of kernels launched in *n_launches if not NULL.
+ * Stream-ordered on `stream`: when the plan's kernels are short (< 128 MB of shot bytes each on
+ * average) they are forked onto side streams owned by the plan and joined back before the call
+ * returns, so work queued on `stream` afterwards sees complete tallies (QCUT_SIDE_STREAMS=0..3
+ * overrides the number of side streams).  Calls on the same plan from several host threads are
+ * serialised over those side streams. */
 int qcut_tally_launch(const qcut_plan* plan, const qcut_schedule* schedule, const uint8_t* d_data,
                       int64_t* d_tallies, int64_t n_tallies, void* stream, int* n_launches);
 

@@ -103,7 +103,8 @@ int qcut_device_count(void);
  *   0 = generic (any width), 1 = bit-sliced with run-time masks, >= 2 = bit-sliced kernels
  *   specialised by NVRTC for the groups' masks: one kernel per group for the QCUT_MAX_JIT_KERNELS
  *   groups with the most terms (>= 12), multi-group kernels (one __noinline__ function per group)
- *   for the other groups with rows of <= 8 bytes; what is left uses kernel 0/1.
+ *   for the other groups with rows of <= 8 bytes; what is left uses kernel 0/1.  Rows of 9..32 bytes
+ *   (65..256 measured qubits in one register) always get a kernel of their own; wider rows use kernel 0.
  * flags: QCUT_PLAN_NO_JIT disables NVRTC specialisation, QCUT_PLAN_GENERIC_ONLY forces kernel 0.
  * Compiled kernels are cached on disk, keyed by a hash of the generated source, the NVRTC version and
  * the options: $QCUT_CACHE_DIR, default $XDG_CACHE_HOME/qcut_b200 or ~/.cache/qcut_b200;

@@ -32,7 +32,7 @@ constexpr uint32_t kMaxJitTerms = 384;  // packed 8-bit counters: ceil(T/4) regi
 
 bool jit_supports(const qcut_group_desc& gd) {
   const uint32_t nb = gd.nb_obs;
-  return nb >= 1 && nb <= 16 && gd.n_terms > 0 && gd.n_terms <= kMaxJitTerms;
+  return nb >= 1 && nb <= 32 && gd.n_terms > 0 && gd.n_terms <= kMaxJitTerms;
 }
 
 // Name of the register holding plane (byte B, bit b) for NB-byte rows (see sliced_prelude.cuh).
@@ -168,9 +168,10 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   os << kPrelude << "\n";
   emit_terms(os, "Terms", gd, masks);
   if (nb > 8) {
-    // Wide rows: 4 warps per CTA, per-warp raw + plane buffers in dynamic shared memory.
+    // Wide rows: 4 warps per CTA (2 for rows of more than 16 bytes), per-warp raw + plane buffers in dynamic
+    // shared memory.
     os << "#ifndef QCUT_HOST_EMU\n"
-          "extern \"C\" __global__ void __launch_bounds__(128, 2)\n"
+          "extern \"C\" __global__ void __launch_bounds__(32 * QcutWide<Terms::NB>::WARPS, 2)\n"
           "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
           "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
           "                  unsigned long long* __restrict__ tallies) {\n"
@@ -501,11 +502,13 @@ int jit_build(qcut_plan* plan, bool load) {
     if (err == cudaSuccess) err = cudaLibraryGetKernel(&jk.kernel, jk.library, "qcut_tally_sliced");
     if (err != cudaSuccess) return cuda_fail(err, "cudaLibraryLoadData(qcut_tally_sliced)");
     if (jk.variants.empty() && jk.nb_obs > 8) {
-      // wide rows: 4 warps per CTA, per warp raw buffer (32 lanes x (4 NB + 1) words) + row / plane store
+      // wide rows: 4 (2 above 16 bytes) warps per CTA, per warp raw buffer (32 lanes x (4 NB + 1) words) + row /
+      // plane store -- QcutWide<NB> in sliced_prelude.cuh
       const int blocks = (jk.nb_obs + 3) / 4;
-      jk.threads = 128;
+      const int warps = jk.nb_obs > 16 ? 2 : 4;
+      jk.threads = 32 * warps;
       jk.min_blocks = 2;
-      jk.smem_bytes = 4 * (32 * (4 * jk.nb_obs + 1) + blocks * 32 * 32) * 4;
+      jk.smem_bytes = warps * (32 * (4 * jk.nb_obs + 1) + blocks * 32 * 32) * 4;
       int dev = 0;
       QCUT_CUDA(cudaGetDevice(&dev));
       QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));

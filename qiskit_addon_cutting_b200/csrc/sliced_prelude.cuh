@@ -442,7 +442,7 @@ QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __r
   }
 }
 
-// ---- wide rows (9..16 bytes): rows staged through shared memory, bit-planes parked in shared memory ----
+// ---- wide rows (9..32 bytes): rows staged through shared memory, bit-planes parked in shared memory ----
 // Up to 128 bit-planes do not fit the register file, so the blocks are transposed one at a time and the
 // planes are parked in shared memory ([plane][lane], conflict free); the generated term code then reads
 // planes at *static* shared-memory offsets (`P[p * 32]`).  Rows are cut out of a per-warp raw buffer that
@@ -450,6 +450,7 @@ QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __r
 // contiguous bytes), stored at a stride of 4 * NB + 1 words so that the lanes' row reads hit 32 banks.
 template <int NB>
 struct QcutWide {
+  static const int WARPS = NB > 16 ? 2 : 4;                  // warps per CTA (shared memory per warp grows with NB)
   static const int BLOCKS = (NB + 3) / 4;
   static const int RAW_STRIDE = 4 * NB + 1;                 // words per lane
   static const int RAW_WORDS = 32 * RAW_STRIDE;             // one group of a step (16 shots per lane)
@@ -508,25 +509,31 @@ QCUT_DEV void qcut_lane_tile_wide(const uint8_t* __restrict__ obs, const uint8_t
       {
         const int region_bytes = 512 * NB;  // 32 lanes x 16 shots x NB bytes
         const uint8_t* __restrict__ src = obs_s + (uint64_t)g * region_bytes + (uint64_t)lane * 16;
-        qcut_u4 v[NB];
-        if (full) {
-          // all NB loads are issued back to back (no predicate between a load and its use)
+        int valid = n * NB - g * region_bytes;
+        valid = valid < 0 ? 0 : (valid > region_bytes ? region_bytes : valid);
+        constexpr int CB = NB > 16 ? 16 : NB;  // loads in flight per lane (16 x 16 bytes at most: registers)
 #pragma unroll
-          for (int c = 0; c < NB; ++c) v[c] = qcut_ld16(src + c * 512);
-        } else {
-          int valid = n * NB - g * region_bytes;
-          valid = valid < 0 ? 0 : (valid > region_bytes ? region_bytes : valid);
+        for (int c0 = 0; c0 < NB; c0 += CB) {
+          qcut_u4 v[CB];
+          if (full) {
+            // the loads of a batch are issued back to back (no predicate between a load and its use)
 #pragma unroll
-          for (int c = 0; c < NB; ++c)  // clamped address, not a predicate: the loads stay back to back;
-                                        // chunks past the end only feed rows that valid_rows zeroes
-            v[c] = qcut_ld16((c * 32 + lane) * 16 < valid ? src + c * 512 : obs_s);
-        }
+            for (int c = 0; c < CB; ++c)
+              if (c0 + c < NB) v[c] = qcut_ld16(src + (c0 + c) * 512);
+          } else {
 #pragma unroll
-        for (int c = 0; c < NB; ++c) {
-          const int q = c * 32 + lane;  // 16-byte chunk of the region
-          const int owner = q / NB, pos = q - owner * NB;
-          uint32_t* dst = raw + owner * W::RAW_STRIDE + pos * 4;
-          dst[0] = v[c].x; dst[1] = v[c].y; dst[2] = v[c].z; dst[3] = v[c].w;
+            for (int c = 0; c < CB; ++c)  // clamped address, not a predicate: the loads stay back to back;
+                                          // chunks past the end only feed rows that valid_rows zeroes
+              if (c0 + c < NB) v[c] = qcut_ld16(((c0 + c) * 32 + lane) * 16 < valid ? src + (c0 + c) * 512 : obs_s);
+          }
+#pragma unroll
+          for (int c = 0; c < CB; ++c)
+            if (c0 + c < NB) {
+              const int q = (c0 + c) * 32 + lane;  // 16-byte chunk of the region
+              const int owner = q / NB, pos = q - owner * NB;
+              uint32_t* dst = raw + owner * W::RAW_STRIDE + pos * 4;
+              dst[0] = v[c].x; dst[1] = v[c].y; dst[2] = v[c].z; dst[3] = v[c].w;
+            }
         }
       }
 #else

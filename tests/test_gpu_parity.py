@@ -103,15 +103,31 @@ def test_expvals_on_golden_cases(lib, name):
 
 
 @pytest.mark.parametrize("nbits,qbits", [(3, 1), (8, 8), (9, 2), (16, 1), (17, 3), (24, 9), (31, 1), (33, 4),
-                                          (47, 1), (56, 8), (64, 1), (65, 2), (100, 1), (127, 8), (200, 17)])
+                                          (47, 1), (56, 8), (64, 1), (65, 2), (100, 1), (127, 8), (133, 2), (156, 1),
+                                          (200, 17), (256, 3), (264, 1)])
 @pytest.mark.parametrize("shots", [1, 100, 4096, 5000])
 def test_tallies_every_row_width(lib, nbits, qbits, shots):
-    """Row widths 1..25 bytes (bit-sliced and generic kernels), qpd widths 1..3 bytes, ragged shot counts."""
+    """Row widths 1..33 bytes (bit-sliced kernels up to 32 bytes, generic beyond), qpd widths 1..3 bytes, ragged
+    shot counts."""
     rng = np.random.default_rng(nbits * 7919 + shots)
     observables = {"A": _cases.random_paulis(rng, 20, nbits, 1, min(nbits, 40), "Z")}
     results = _cases.make_results(observables, 2, shots, qbits, seed=int(rng.integers(1 << 30)))
     _, got, want = _device_tallies(results, [(0.5, WeightType.EXACT), (-0.5, WeightType.EXACT)], observables)
     assert np.array_equal(got, want)
+
+
+def test_rows_of_17_to_32_bytes_use_the_specialised_kernel(lib):
+    """A 156-qubit register (20-byte rows) is handled by the wide-row engine, 33-byte rows by the generic kernel."""
+    for nbits, specialised in ((156, True), (256, True), (264, False)):
+        rng = np.random.default_rng(nbits)
+        observables = {"A": _cases.random_paulis(rng, 30, nbits, nbits // 2, nbits, "Z")}  # every qubit is measured
+        results = _cases.make_results(observables, 1, 6000, 1, seed=nbits)
+        batch, got, want = _device_tallies(results, [(1.0, WeightType.EXACT)], observables)
+        assert np.array_equal(got, want)
+        assert batch.tables.groups["nb_obs"].tolist() == [(nbits + 7) // 8]
+        assert (max(batch.plan.kernels()) >= _lib.KERNEL_JIT0) == specialised
+        if specialised:
+            assert "qcut_lane_tile_wide" in batch.plan.source(_lib.KERNEL_JIT0)
 
 
 def test_empty_pubs_and_zero_shots(lib):

@@ -74,14 +74,16 @@ def test_nvrtc_compiles_golden_plans_for_sm100a(lib):
 
 
 def test_unsupported_widths_are_not_specialised(lib):
-    groups = np.zeros(3, dtype=_lib.GROUP_DTYPE)
-    groups[0] = (2, 17, 0, 0)    # 17-byte rows: generic kernel
-    groups[1] = (2, 8, 34, 0)    # 8-byte rows
-    groups[2] = (2, 16, 50, 0)   # 16-byte rows: wide-row specialised kernel
-    masks = np.arange(82, dtype=np.uint8)
+    groups = np.zeros(4, dtype=_lib.GROUP_DTYPE)
+    groups[0] = (2, 33, 0, 0)    # 33-byte rows: generic kernel
+    groups[1] = (2, 8, 66, 0)    # 8-byte rows
+    groups[2] = (2, 16, 82, 0)   # 16-byte rows: wide-row specialised kernel
+    groups[3] = (2, 32, 114, 0)  # 32-byte rows: wide-row specialised kernel, 2 warps per CTA
+    masks = np.arange(178, dtype=np.uint8)
     assert _lib.generate_source(groups, masks, 0) == ""
     assert "struct Terms" in _lib.generate_source(groups, masks, 1)
     assert "qcut_lane_tile_wide" in _lib.generate_source(groups, masks, 2)
+    assert "qcut_lane_tile_wide" in _lib.generate_source(groups, masks, 3)
 
 
 def _guarded_copy(data: np.ndarray, used: int):
@@ -118,10 +120,11 @@ def test_emulated_loads_stay_inside_the_promised_slack(lib, nbits, qbits, shots)
     del guarded
 
 
-@pytest.mark.parametrize("nbits,qbits", [(65, 1), (72, 3), (81, 1), (96, 2), (100, 9), (111, 1), (120, 4), (127, 8), (128, 1)])
+@pytest.mark.parametrize("nbits,qbits", [(65, 1), (72, 3), (81, 1), (96, 2), (100, 9), (111, 1), (120, 4), (127, 8), (128, 1),
+                                         (129, 1), (133, 2), (156, 1), (160, 3), (191, 1), (200, 9), (233, 1), (256, 1)])
 @pytest.mark.parametrize("shots", [7, 1024, 1500, 4100])
 def test_emulated_wide_row_kernel(lib, nbits, qbits, shots):
-    """Rows of 9..16 bytes: shared-memory staged rows + parked planes (specialised kernels only)."""
+    """Rows of 9..32 bytes: shared-memory staged rows + parked planes (specialised kernels only)."""
     rng = np.random.default_rng(nbits * 31 + shots)
     observables = {"A": _cases.random_paulis(np.random.default_rng(nbits), 11, nbits, 1, min(nbits, 50), "Z")}
     coefficients = [(1.0, WeightType.EXACT)]
@@ -129,6 +132,6 @@ def test_emulated_wide_row_kernel(lib, nbits, qbits, shots):
     tables, data, want = _stage_host(results, coefficients, observables)
     mm, guarded = _guarded_copy(data, tables.data_bytes)
     got, covered = _host_emu.emulate_tallies(tables, guarded, "jit")
-    assert covered.all(), "rows of 9..16 bytes must be covered by the specialised kernels"
+    assert covered.all(), "rows of 9..32 bytes must be covered by the specialised kernels"
     assert np.array_equal(got, want)
     del guarded

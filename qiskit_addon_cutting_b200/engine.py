@@ -304,6 +304,13 @@ class DeviceBatch:
 # Ingestion of SamplerV2 results: borrowed BitArray buffers -> pinned staging -> HBM
 # ------------------------------------------------------------------------------------------------
 _pinned: dict[int, torch.Tensor] = {}
+_staging_locks: dict[int, threading.Lock] = {}
+_staging_locks_guard = threading.Lock()
+
+
+def _staging_lock(device: int) -> threading.Lock:
+    with _staging_locks_guard:
+        return _staging_locks.setdefault(device, threading.Lock())
 
 
 def _pinned_buffer(nbytes: int) -> torch.Tensor:
@@ -567,20 +574,23 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
     """
     _lib.require_device()
     t_start = time.perf_counter()
-    stager = _BlockStager()
-    try:
-        tables, _ = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, sink=stager,
-                                      block_pubs=_BLOCK_PUBS)
-    except BaseException:
-        stager.finish(raise_errors=False)
-        raise
-    # plan lookup / schedule upload proceed while the last blocks are still in flight
-    t_walked = time.perf_counter()
-    try:
-        batch = DeviceBatch(tables, stager, flags=flags)
-    finally:
-        t_batch = time.perf_counter()
-        stager.finish(raise_errors=False)
+    # The pinned ring is shared by the calls of a process on one device: concurrent callers (Python threads)
+    # take turns for the staging phase -- it is PCIe bound anyway -- and run their kernels independently.
+    with _staging_lock(torch.cuda.current_device()):
+        stager = _BlockStager()
+        try:
+            tables, _ = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, sink=stager,
+                                          block_pubs=_BLOCK_PUBS)
+        except BaseException:
+            stager.finish(raise_errors=False)
+            raise
+        # plan lookup / schedule upload proceed while the last blocks are still in flight
+        t_walked = time.perf_counter()
+        try:
+            batch = DeviceBatch(tables, stager, flags=flags)
+        finally:
+            t_batch = time.perf_counter()
+            stager.finish(raise_errors=False)
     if stager.error is not None:
         raise stager.error
     global last_stage_trace

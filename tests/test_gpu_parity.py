@@ -195,3 +195,29 @@ def test_block_staging_many_blocks(lib, monkeypatch, name):
     out = reconstruct_expectation_values(results, coefficients, observables)
     monkeypatch.undo()
     assert _hex(out) == _hex(reconstruct_expectation_values(results, coefficients, observables))
+
+
+def test_concurrent_calls_from_python_threads(lib):
+    """The reference is pure; ours must at least be safe to call from several threads (shared pinned ring, plan
+    cache and side streams are serialised internally): every thread gets the result of its own inputs."""
+    import threading
+
+    cases = [_cases.SMALL_CASES[name]() for name in ("molecular", "odd_widths", "wire", "heavy_hex")]
+    want = [_hex(reconstruct_expectation_values(*c)) for c in cases]
+    got: list = [None] * (3 * len(cases))
+    errors: list = []
+
+    def work(slot):
+        try:
+            for _ in range(3):
+                got[slot] = _hex(reconstruct_expectation_values(*cases[slot % len(cases)]))
+        except BaseException as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(got))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert got == [want[i % len(cases)] for i in range(len(got))]

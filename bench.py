@@ -52,10 +52,10 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's loop (the reference is single-threaded pure Python)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(workload, tables, host_bytes_of_pub, seconds: float):
-    """Pick (pub index, shots) pairs worth ~`seconds` of the reference's Python loop (2.7 us/shot + 0.13 us/term)."""
+def cpu_sample(workload, tables, host_bytes_of_pub, seconds: float, count: int = 64):
+    """Pick `count` (pub index, shots) pairs worth ~`seconds` of the reference's Python loop (2.7 us/shot + 0.13 us/term)."""
     sample, budget = [], seconds
-    order = np.linspace(0, len(tables.pubs) - 1, num=min(len(tables.pubs), 64), dtype=np.int64)
+    order = np.linspace(0, len(tables.pubs) - 1, num=min(len(tables.pubs), count), dtype=np.int64)
     per_pub = seconds / len(order)
     for p in order:
         pub = tables.pubs[p]
@@ -104,7 +104,25 @@ def synthetic_fetch(workload, tables, seed):
     return fetch
 
 
+_REF_STATE: dict = {}  # inherited by the forked workers of the reference arm
+
+
+def _reference_worker(job):
+    """One process of the reference arm: the python port of the reference loop on its share of the sample."""
+    index, sample = job
+    fetch = synthetic_fetch(_REF_STATE["workload"], _REF_STATE["tables"], _REF_STATE["workload"].seed + 7919 * index)
+    return run_reference_port(_REF_STATE["tables"], sample, fetch)
+
+
 def reference_arm(args):
+    """The reference's CPU implementation of the path on this box's host cores.
+
+    The reference cannot be installed here (no qiskit wheels), so this is the oracle's literal Python port of its
+    loop.  The reference itself is single-threaded; "all the host threads it can use" is realised the only way a
+    user could: one process per core, each reconstructing its own PUBs (they are independent).
+    """
+    import multiprocessing as mp
+
     import workloads as W
 
     rank = int(os.environ.get("RANK", "0"))
@@ -112,25 +130,30 @@ def reference_arm(args):
         return
     w = W.get_workload(args.workload, args.scale)
     tables = W.build_tables(w)
-    # a bounded sample per step so that warmup + steps end within a few minutes
+    n_procs = max(1, int(os.environ.get("QCUT_REF_PROCS", "0") or 0) or (os.cpu_count() or 1))
+    # a bounded sample per step and process so that warmup + steps end within a few minutes
     seconds = min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup))
-    sample = cpu_sample(w, tables, None, seconds)
-    fetch = synthetic_fetch(w, tables, w.seed)
-    for _ in range(args.warmup):
-        run_reference_port(tables, sample[:2], fetch)
+    sample = cpu_sample(w, tables, None, seconds * n_procs, count=n_procs * max(1, -(-64 // n_procs)))  # equal shares
+    jobs = [(i, sample[i::n_procs]) for i in range(n_procs) if sample[i::n_procs]]
+    _REF_STATE.update(workload=w, tables=tables)
     work = secs = 0.0
-    for _ in range(args.steps):
-        wk, s = run_reference_port(tables, sample, fetch)
-        work += wk
-        secs += s
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        for _ in range(args.warmup):
+            pool.map(_reference_worker, [(i, part[:1]) for i, part in jobs])
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            parts = pool.map(_reference_worker, jobs)
+            secs += time.perf_counter() - t0  # wall clock of the slowest process
+            work += sum(wk for wk, _ in parts)
     value = work / secs
-    sample_desc = f"{len(sample)} PUBs x ~{sample[0][1]} shots of {args.workload} per step (python port of the reference loop)"
+    sample_desc = (f"{len(sample)} PUBs x ~{sample[0][1]} shots of {args.workload} per step over {len(jobs)} processes "
+                   f"(python port of the reference loop, one process per core)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8->int64 tallies, f64 sums", "data": "synthetic",
         "config": dict(w.describe(), l2="n/a (cpu)"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(jobs), "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))

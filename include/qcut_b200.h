@@ -124,8 +124,10 @@ size_t qcut_plan_source(const qcut_plan* plan, int kernel, char* buf, size_t buf
 /* ---- schedule -----------------------------------------------------------------------------------
  * Copies the PUB table to HBM and cuts every PUB into tiles of QCUT_TILE_SHOTS consecutive shots,
  * listed per kernel so that each K1 kernel streams only its own tiles.  The two descriptor buffers
- * come from a small per-process cache (destroy waits for the device, then parks them for the next
- * schedule: cudaFree per call was measured at up to 165 ms). */
+ * come from a small per-process cache (cudaFree per call was measured at up to 165 ms).  Destroy never blocks:
+ * it records an event on the stream of the schedule's last qcut_tally_launch and parks the buffers with it, so
+ * launches that read qcut_schedule_device_pubs() must have been queued on that stream (or have completed)
+ * before qcut_schedule_destroy is called. */
 int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int64_t n_pubs,
                          qcut_schedule** out_schedule);
 void qcut_schedule_destroy(qcut_schedule* schedule);

@@ -24,16 +24,17 @@ int cuda_fail(cudaError_t err, const char* what) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = 148;
+  // per device: a process may drive several (different) GPUs
+  constexpr int kMaxDevices = 64;
+  static std::atomic<int> cached[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev].store(n, std::memory_order_relaxed);
   }
-  return cached;
+  return n;
 }
 
 // defined in tally_generic.cu / tally_sliced.cu / reduce.cu / jit.cu
@@ -253,7 +254,9 @@ namespace {
 // Descriptor buffers of schedules are recycled: a schedule lives for one reconstruction call, and
 // cudaFree of its (few MB) buffers was measured at up to 165 ms on a busy device -- half of an
 // end-to-end call.  Freed buffers wait here (a handful per device) for the next schedule.
-struct CachedBuffer { void* ptr; size_t bytes; int device; };
+// `ready` (may be null) completes when the last launch that reads the buffer has finished: the buffer is
+// parked without waiting and whoever takes it next waits on the event (normally long complete).
+struct CachedBuffer { void* ptr; size_t bytes; int device; cudaEvent_t ready; };
 std::mutex g_cache_mutex;
 std::vector<CachedBuffer> g_cache;
 constexpr size_t kCacheEntries = 8;
@@ -269,9 +272,14 @@ cudaError_t cached_alloc(void** ptr, size_t bytes, size_t* capacity, int device)
         best = i;
     }
     if (best >= 0) {
-      *ptr = g_cache[(size_t)best].ptr;
-      *capacity = g_cache[(size_t)best].bytes;
+      const CachedBuffer hit = g_cache[(size_t)best];
       g_cache.erase(g_cache.begin() + best);
+      *ptr = hit.ptr;
+      *capacity = hit.bytes;
+      if (hit.ready) {
+        cudaEventSynchronize(hit.ready);
+        cudaEventDestroy(hit.ready);
+      }
       return cudaSuccess;
     }
   }
@@ -279,18 +287,27 @@ cudaError_t cached_alloc(void** ptr, size_t bytes, size_t* capacity, int device)
   return cudaMalloc(ptr, bytes);
 }
 
-void cached_release(void* ptr, size_t bytes, int device) {
-  if (!ptr) return;
-  void* evict = nullptr;
+void cached_release(void* ptr, size_t bytes, int device, cudaEvent_t ready) {
+  if (!ptr) {
+    if (ready) cudaEventDestroy(ready);
+    return;
+  }
+  CachedBuffer evict{nullptr, 0, 0, nullptr};
   {
     std::lock_guard<std::mutex> lock(g_cache_mutex);
-    g_cache.push_back(CachedBuffer{ptr, bytes, device});
+    g_cache.push_back(CachedBuffer{ptr, bytes, device, ready});
     if (g_cache.size() > kCacheEntries) {
-      evict = g_cache.front().ptr;
+      evict = g_cache.front();
       g_cache.erase(g_cache.begin());
     }
   }
-  if (evict) cudaFree(evict);
+  if (evict.ptr) {
+    if (evict.ready) {
+      cudaEventSynchronize(evict.ready);
+      cudaEventDestroy(evict.ready);
+    }
+    cudaFree(evict.ptr);  // synchronises with the device by itself
+  }
 }
 }  // namespace
 
@@ -363,16 +380,29 @@ int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int
 
 void qcut_schedule_destroy(qcut_schedule* schedule) {
   if (!schedule) return;
-  // Like the cudaFree it replaces, wait for launches that may still read the descriptors before the
-  // buffers can be handed to the next schedule (idle device: microseconds).
-  int current = -1;
-  if (cudaGetDevice(&current) == cudaSuccess) {
-    if (current != schedule->device) cudaSetDevice(schedule->device);
-    cudaDeviceSynchronize();
-    if (current != schedule->device) cudaSetDevice(current);
+  // Launches that read the descriptors may still be in flight.  Nothing waits here: an event recorded on the
+  // stream of the schedule's last qcut_tally_launch (which also orders every later launch the caller queued on
+  // that stream, e.g. qcut_reduce_launch reading d_pubs) travels with the parked buffers, and the next schedule
+  // that takes them waits on it.  Only if that is impossible (foreign device, dead stream) the device is drained.
+  cudaEvent_t ready[2] = {nullptr, nullptr};
+  if (schedule->launched) {
+    int current = -1;
+    bool ok = cudaGetDevice(&current) == cudaSuccess;
+    if (ok && current != schedule->device) ok = cudaSetDevice(schedule->device) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i) {
+      ok = cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventRecord(ready[i], schedule->last_stream) == cudaSuccess;
+    }
+    if (!ok) {
+      cudaGetLastError();
+      for (cudaEvent_t& e : ready)
+        if (e) { cudaEventDestroy(e); e = nullptr; }
+      cudaDeviceSynchronize();
+    }
+    if (current >= 0 && current != schedule->device) cudaSetDevice(current);
   }
-  cached_release(schedule->d_pubs, schedule->pubs_capacity, schedule->device);
-  cached_release(schedule->d_tiles, schedule->tiles_capacity, schedule->device);
+  cached_release(schedule->d_pubs, schedule->pubs_capacity, schedule->device, ready[0]);
+  cached_release(schedule->d_tiles, schedule->tiles_capacity, schedule->device, ready[1]);
   delete schedule;
 }
 
@@ -392,6 +422,8 @@ int qcut_tally_launch(const qcut_plan* plan, const qcut_schedule* schedule, cons
   if ((int)schedule->kernel_tile_begin.size() != plan->n_kernels() + 1)
     return set_error("qcut_tally_launch: schedule was built for a different plan"), QCUT_ERR_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  schedule->last_stream = s;
+  schedule->launched = true;
   if (n_tallies > 0) QCUT_CUDA(cudaMemsetAsync(d_tallies, 0, sizeof(int64_t) * (size_t)n_tallies, s));
   int active = 0;
   int64_t total_bytes = 0;

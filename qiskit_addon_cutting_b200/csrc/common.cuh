@@ -87,4 +87,8 @@ struct qcut_schedule {
   int device = 0;
   std::vector<int64_t> kernel_tile_begin;  // n_kernels + 1 offsets into d_tiles
   std::vector<int64_t> kernel_bytes;       // shot bytes each kernel reads (decides whether launches overlap)
+  // stream of the most recent qcut_tally_launch: qcut_schedule_destroy records an event there instead of
+  // draining the device (the descriptors are recycled once that event has completed)
+  mutable cudaStream_t last_stream = nullptr;
+  mutable bool launched = false;
 };

@@ -20,7 +20,7 @@ from collections.abc import Mapping, Sequence
 
 import numpy as np
 
-from .observable_grouping import CommutingObservableGroup, ObservableCollection
+from .observable_grouping import ObservableCollection
 
 __all__ = ["reconstruct_expectation_values"]
 
@@ -54,21 +54,6 @@ def _has_phase(observables) -> bool:
     if phase is not None and np.ndim(phase) == 1:
         return bool(np.any(np.asarray(phase) != 0))
     return any(obs.phase != 0 for obs in observables)
-
-
-def _get_pauli_indices(cog: CommutingObservableGroup) -> list[int]:
-    """Qubits measured for a group; identity-only groups measure qubit 0 (reference ``cutting_experiments.py:362-370``)."""
-    return cog.pauli_indices if cog.pauli_indices else [0]
-
-
-def _outcome_to_int(outcome) -> int:
-    """Reference ``cutting_reconstruction.py:225-232``."""
-    if isinstance(outcome, (int, np.integer)):
-        return int(outcome)
-    outcome = outcome.replace(" ", "")
-    if len(outcome) < 2 or outcome[1] in ("0", "1"):
-        return int(f"0b{outcome}", 0)
-    return int(outcome, 0)
 
 
 _collection_cache: dict = {}
@@ -131,9 +116,11 @@ def reconstruct_expectation_values(
         observables: a ``PauliList`` or a dict mapping partition labels to ``PauliList``\ s.
         process_group: optional ``torch.distributed`` process group (e.g. ``dist.group.WORLD``).
             When given, every rank must make the same call; each rank processes a contiguous
-            slice of ``coefficients`` (for every subsystem) and the partial sums are all-reduced
-            over NCCL, so every rank returns the full result.  Without it the call is
-            single-process, exactly like the reference.
+            slice of ``coefficients`` (for every subsystem, balanced by shot bytes) and the partial
+            sums are all-reduced over NCCL, so every rank returns the full result; with fewer
+            coefficients than balanced slices need, the ranks split the PUBs by bytes instead and
+            all-reduce the exact int64 tally table (``distributed`` module docstring).  Without it
+            the call is single-process, exactly like the reference.
 
     Returns:
         ``list`` of ``numpy.float64``, one expectation value per input observable.
@@ -167,16 +154,68 @@ def reconstruct_expectation_values(
         )
 
     # Everything below needs the CUDA library and a device; no CPU fallback exists.
-    from . import distributed, engine, quasi
+    import torch
+
+    from . import _lib, distributed, engine, quasi
 
     rank, world = distributed.rank_and_world(process_group)
-    i_lo, i_hi = distributed.coefficient_slice(len(coeffs), rank, world)
     result_list = [results_dict[label] for label in labels]
     collection_list = [collections[label] for label in labels]
-    if all(v1) and labels:
-        out = quasi.reconstruct_v1(result_list, collection_list, coeffs, i_lo, i_hi, n_obs)
+    if world == 1:
+        if len(coeffs) == 0 or not labels:
+            return list(np.zeros(n_obs))  # the reference's loops do not execute: expvals stay 0 (:133-170)
+        if all(v1):
+            out = quasi.reconstruct_v1(result_list, collection_list, coeffs, 0, len(coeffs), n_obs)
+        else:
+            out = engine.stage_v2(result_list, collection_list, coeffs, 0, len(coeffs), n_obs).run()
+        return list(out.cpu().numpy())
+
+    # ---- sharded over the ranks of the process group: every rank makes the same call -----------------
+    # A rank that fails keeps taking part in the collective (zeros + an error flag in the spare last element), so
+    # that all ranks raise together instead of the healthy ones hanging in NCCL.
+    _lib.require_device()
+    error: BaseException | None = None
+    out = None
+    mode = "coefficients"
+    try:
+        sharding = engine.plan_sharding(result_list, collection_list, len(coeffs), rank, world,
+                                        allow_tally_mode=not any(v1))
+        mode = sharding.mode
+    except Exception as exc:  # noqa: BLE001 - re-raised below, after the collective
+        error = exc
+    if error is None and mode == "tallies":
+        # few coefficients: byte-balanced (label, PUB, shot range) pieces, all-reduce of the int64 tally table
+        batch = None
+        try:
+            batch = engine.stage_v2_pieces(result_list, collection_list, coeffs, n_obs, rank, world,
+                                           collected=sharding.collected)
+        except Exception as exc:  # noqa: BLE001
+            error = exc
+        if batch is not None:
+            out = batch.run_tally_sharded(process_group, world)
+        else:
+            n_tallies = len(coeffs) * sum(len(g.pauli_bitmasks) for c in collection_list for g in c.groups)
+            table = torch.zeros(n_tallies + 1, dtype=torch.int64, device="cuda")
+            distributed.all_reduce_with_flag(table, True, process_group, world)
     else:
-        batch = engine.stage_v2(result_list, collection_list, coeffs, i_lo, i_hi, n_obs)
-        out = batch.run()
-    out = distributed.all_reduce_sum(out, process_group, world)
-    return list(out.cpu().numpy())
+        if error is None:
+            try:
+                if sharding.i_hi > sharding.i_lo and labels:
+                    if all(v1):
+                        part = quasi.reconstruct_v1(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs)
+                    else:
+                        part = engine.stage_v2(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs,
+                                               collected=sharding.collected or None).run()
+                    out = torch.zeros(n_obs + 1, dtype=torch.float64, device="cuda")
+                    out[:n_obs] = part
+            except Exception as exc:  # noqa: BLE001
+                error = exc
+                out = None
+        if out is None:  # empty slice (more ranks than coefficients) or a local failure: contribute zeros
+            out = torch.zeros(n_obs + 1, dtype=torch.float64, device="cuda")
+        distributed.all_reduce_with_flag(out, error is not None, process_group, world)
+    if error is not None:
+        raise error
+    host = out.cpu().numpy()
+    distributed.check_flag(host[-1])
+    return list(host[:n_obs])

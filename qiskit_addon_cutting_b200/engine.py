@@ -37,10 +37,24 @@ def _stream_ptr() -> int:
 
 def _to_device(a: np.ndarray) -> torch.Tensor:
     """Copy a (possibly structured) numpy array to the current CUDA device as raw bytes."""
-    raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-    if raw.size == 0:
-        return torch.zeros(16, dtype=torch.uint8, device="cuda")
-    return torch.from_numpy(raw.copy()).to("cuda", non_blocking=False)
+    return _upload_packed([a])[0]
+
+
+def _upload_packed(arrays: list[np.ndarray]) -> list[torch.Tensor]:
+    """Several (possibly structured) numpy tables -> ONE host-to-device copy; returns a byte view per table.
+
+    A reconstruction call uploads four or five small descriptor tables; one packed copy instead of one
+    synchronous copy each matters for the small configurations (tens of microseconds per copy)."""
+    raws = [np.ascontiguousarray(a).view(np.uint8).reshape(-1) for a in arrays]
+    starts, total = [], 0
+    for r in raws:
+        starts.append(total)
+        total += max(_align(r.size), _ALIGN)
+    packed = np.zeros(total, dtype=np.uint8)
+    for r, o in zip(raws, starts):
+        packed[o: o + r.size] = r
+    dev = torch.from_numpy(packed).to("cuda", non_blocking=False)
+    return [dev[o: o + max(_align(r.size), _ALIGN)] for r, o in zip(raws, starts)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -235,17 +249,23 @@ class Schedule:
 class DeviceBatch:
     """One rank's share of a reconstruction, resident in HBM."""
 
-    def __init__(self, tables: HostTables, data: torch.Tensor, *, flags: int = 0):
+    def __init__(self, tables: HostTables, data, *, flags: int = 0, k1_pubs: np.ndarray | None = None):
+        """``k1_pubs`` (tally-table sharding): the PUB pieces THIS rank tallies -- descriptors with this rank's
+        data offsets and shot counts but the global ``tally_offset`` -- while ``tables.pubs`` stays the complete
+        table the product/sum kernel reads after the tally table has been all-reduced."""
         self.tables = tables
         self.plan = get_plan(tables.groups, tables.masks, flags=flags)
-        self.schedule = Schedule(self.plan, tables.pubs)
+        self.schedule = Schedule(self.plan, tables.pubs if k1_pubs is None else k1_pubs)
         self.data = data
-        self.labels = _to_device(tables.labels)
-        self.lookup_start = _to_device(tables.lookup_start)
-        self.lookup = _to_device(tables.lookup)
-        self.coeffs = _to_device(tables.coeffs)
-        self.tallies = torch.empty(max(tables.n_tallies, 1), dtype=torch.int64, device="cuda")
-        self.out = torch.empty(max(tables.n_obs, 1), dtype=torch.float64, device="cuda")
+        small = [tables.labels, tables.lookup_start, tables.lookup, tables.coeffs]
+        if k1_pubs is not None:
+            small.append(tables.pubs)
+        dev = _upload_packed(small)
+        self.labels, self.lookup_start, self.lookup, self.coeffs = dev[:4]
+        self.k2_pubs = dev[4] if k1_pubs is not None else None
+        # one spare element each: the error flag of the collectives (distributed.all_reduce_with_flag)
+        self.tallies = torch.empty(tables.n_tallies + 1, dtype=torch.int64, device="cuda")
+        self.out = torch.empty(tables.n_obs + 1, dtype=torch.float64, device="cuda")
         ws = _lib.load().qcut_reduce_workspace_bytes(len(tables.coeffs), tables.n_obs)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device="cuda")
         self.tally_launches = 0
@@ -274,7 +294,7 @@ class DeviceBatch:
         check(
             _lib.load().qcut_reduce_launch(
                 self.tallies.data_ptr(),
-                self.schedule.d_pubs,
+                self.schedule.d_pubs if self.k2_pubs is None else self.k2_pubs.data_ptr(),
                 self.labels.data_ptr(),
                 len(t.labels),
                 self.lookup_start.data_ptr(),
@@ -298,6 +318,18 @@ class DeviceBatch:
         self.launch_tally()
         self.launch_reduce()
         return self.out[: self.tables.n_obs]
+
+    def run_tally_sharded(self, process_group, world: int) -> torch.Tensor:
+        """Tally-table sharding: K1 on this rank's pieces, all-reduce of the int64 table (+ error flag), K2 on the
+        complete table.  Every rank ends up with the full, bit-identical result."""
+        from . import distributed
+
+        self.launch_tally()
+        self.tallies[-1] = 0
+        distributed.all_reduce_with_flag(self.tallies, False, process_group, world)
+        self.launch_reduce()
+        self.out[-1] = self.tallies[-1].to(torch.float64)
+        return self.out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -377,7 +409,7 @@ class HostArrays:
 
 
 def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int,
-                      n_obs: int, *, sink=None, block_pubs: int = 0) -> tuple[HostTables, HostArrays]:
+                      n_obs: int, *, sink=None, block_pubs: int = 0, collected: dict | None = None) -> tuple[HostTables, HostArrays]:
     """Walk the PUBs of coefficient range ``[i_lo, i_hi)`` of every label (host only, no device).
 
     Offsets, tally slots and group variants are computed with NumPy, not per PUB.  The walk proceeds in
@@ -395,6 +427,7 @@ def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndar
     for result, collection in zip(results_by_label, collections):
         n_groups = len(collection.groups)
         li = builder.add_label(collection, n_pubs)
+        walked = collected.get(li) if collected else None  # (keep, obs_ptr, ...) of ALL PUBs of the label
         terms_of_group = np.array([builder.n_terms(li, g) for g in range(n_groups)], dtype=np.int64)
         p_lo, p_hi = i_lo * n_groups, i_hi * n_groups
         step = block_pubs if block_pubs > 0 else max(p_hi - p_lo, 1)
@@ -403,7 +436,11 @@ def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndar
             b_lo, b_hi = b_hi, min(b_hi + step, p_hi)
             if sink is not None:
                 step *= 4  # every hand-over costs the sink a pipeline fill: few, growing blocks
-            keep, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd = _collect_label(result, b_lo, b_hi)
+            if walked is None:
+                keep, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd = _collect_label(result, b_lo, b_hi)
+            else:
+                keep = walked[0][2 * b_lo: 2 * b_hi]
+                obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd = (a[b_lo:b_hi] for a in walked[1:])
             n = b_hi - b_lo
             g_idx = np.arange(b_lo, b_hi, dtype=np.int64) % n_groups
             # group variants: one per distinct (group, row width)
@@ -412,7 +449,7 @@ def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndar
             for k in np.unique(key).tolist():
                 variant[key == k] = builder.group_variant(li, k >> 32, k & 0xFFFFFFFF)
             terms = terms_of_group[g_idx]
-            if int(shots.max()) >= 2**31:
+            if n and int(shots.max()) >= 2**31:
                 raise ValueError("A PUB with 2**31 or more shots is not supported.")
             raw = np.empty(2 * n, dtype=np.int64)
             raw[0::2] = shots * nb_obs
@@ -564,23 +601,62 @@ class _BlockStager:
         return self.base
 
 
+_SIMPLE_PUBS = 8192          # up to this many PUBs the whole call is walked first ...
+_SIMPLE_BYTES = 64 << 20      # ... and staged by one gather + one H2D copy if it is at most this large
+_copy_done: dict[int, torch.cuda.Event] = {}  # per device: last H2D copy out of the pinned buffer
+
+
+def _stage_simple(tables: HostTables, arrays: HostArrays) -> torch.Tensor:
+    """Small inputs: gather every borrowed buffer into the pinned buffer, ONE host-to-device copy on the current
+    stream.  No threads are started and nothing is pipelined: for the tutorial-sized calls the pipeline's fixed
+    costs (two feeder threads, a ring, one event per slot) were the larger part of the call."""
+    dev = torch.cuda.current_device()
+    n = tables.data_bytes
+    pinned = _pinned_buffer(max(n, 1 << 20))
+    done = _copy_done.get(dev)
+    if done is not None:
+        done.synchronize()  # a previous call's copy may still be reading the pinned buffer
+    gather_arrays(tables, arrays, pinned.data_ptr(), n_threads=1 if n <= (4 << 20) else 8)
+    data = torch.empty(n + _lib.DATA_SLACK, dtype=torch.uint8, device="cuda")
+    data[:n].copy_(pinned[:n], non_blocking=True)
+    ev = _copy_done.get(dev) or torch.cuda.Event()
+    ev.record()
+    _copy_done[dev] = ev
+    return data
+
+
 def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
-             *, flags: int = 0) -> DeviceBatch:
+             *, flags: int = 0, collected: dict | None = None) -> DeviceBatch:
     """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM.
 
-    The PUBs are walked block by block (``csrc/pyhelper.c``); a background thread hands every walked block to
-    ``qcut_stage_h2d``, whose worker threads gather runs of borrowed ``BitArray`` buffers into a small pinned
-    ring and queue one H2D copy per run: attribute walk, host gather and PCIe transfer all overlap.
+    Large inputs: the PUBs are walked block by block (``csrc/pyhelper.c``); background threads hand every walked
+    block to ``qcut_stage_h2d``, whose worker threads gather runs of borrowed ``BitArray`` buffers into a small
+    pinned ring and queue one H2D copy per run: attribute walk, host gather and PCIe transfer all overlap.
+    Small inputs (<= 8192 PUBs and <= 64 MiB): one walk, one gather, one copy (``_stage_simple``).
     """
     _lib.require_device()
     t_start = time.perf_counter()
+    n_pubs = (i_hi - i_lo) * sum(len(c.groups) for c in collections)
+    global last_stage_trace
+    if n_pubs <= _SIMPLE_PUBS:
+        tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, collected=collected)
+        if tables.data_bytes <= _SIMPLE_BYTES:
+            t_walked = time.perf_counter()
+            with _staging_lock(torch.cuda.current_device()):
+                data = _stage_simple(tables, arrays)
+            t_staged = time.perf_counter()
+            batch = DeviceBatch(tables, data, flags=flags)
+            batch.keepalive = arrays.keep
+            last_stage_trace = {"walk_s": t_walked - t_start, "stage_s": t_staged - t_walked,
+                                "tables_s": time.perf_counter() - t_staged, "path": "simple"}
+            return batch
     # The pinned ring is shared by the calls of a process on one device: concurrent callers (Python threads)
     # take turns for the staging phase -- it is PCIe bound anyway -- and run their kernels independently.
     with _staging_lock(torch.cuda.current_device()):
         stager = _BlockStager()
         try:
             tables, _ = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, sink=stager,
-                                          block_pubs=_BLOCK_PUBS)
+                                          block_pubs=_BLOCK_PUBS, collected=collected)
         except BaseException:
             stager.finish(raise_errors=False)
             raise
@@ -593,12 +669,108 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
             stager.finish(raise_errors=False)
     if stager.error is not None:
         raise stager.error
-    global last_stage_trace
     last_stage_trace = {
         "walk_s": t_walked - t_start, "tables_s": t_batch - t_walked, "wait_s": time.perf_counter() - t_batch,
-        "blocks": [(b, s - t_start, e - t_start) for b, s, e in stager.block_seconds],
+        "blocks": [(b, s - t_start, e - t_start) for b, s, e in stager.block_seconds], "path": "pipelined",
     }
     return batch
+
+
+def stage_v2_pieces(results_by_label: list, collections: list, coeffs: np.ndarray, n_obs: int, rank: int,
+                    world: int, *, flags: int = 0, collected: dict | None = None) -> DeviceBatch:
+    """Tally-table sharding (``distributed`` module docstring): every rank describes ALL PUBs (descriptors only),
+    stages the bytes of its own byte-balanced piece of the flattened (label, PUB, shot range) list and tallies it
+    into the global tally table."""
+    from . import distributed
+
+    _lib.require_device()
+    tables, arrays = build_host_tables(results_by_label, collections, coeffs, 0, len(coeffs), n_obs, collected=collected)
+    pubs = tables.pubs
+    nb_obs = tables.groups["nb_obs"][pubs["group"]].astype(np.int64) if len(pubs) else np.zeros(0, dtype=np.int64)
+    nb_qpd = pubs["nb_qpd"].astype(np.int64)
+    pieces = distributed.piece_ranges(nb_obs + nb_qpd, pubs["shots"], world, TILE_SHOTS)[rank]
+    k1 = np.zeros(len(pieces), dtype=PUB_DTYPE)
+    src = np.zeros(2 * len(pieces), dtype=np.uint64)
+    nbytes = np.zeros(2 * len(pieces), dtype=np.uint64)
+    dst = np.zeros(2 * len(pieces), dtype=np.uint64)
+    offset = 0
+    for j, (p, lo, hi) in enumerate(pieces):
+        n = hi - lo
+        o_bytes, q_bytes = n * int(nb_obs[p]), n * int(nb_qpd[p])
+        k1[j] = pubs[p]
+        k1[j]["shots"] = n
+        k1[j]["obs_offset"] = offset
+        src[2 * j], nbytes[2 * j], dst[2 * j] = int(arrays.src[2 * p]) + lo * int(nb_obs[p]), o_bytes, offset
+        offset += _align(o_bytes)
+        k1[j]["qpd_offset"] = offset
+        src[2 * j + 1], nbytes[2 * j + 1], dst[2 * j + 1] = int(arrays.src[2 * p + 1]) + lo * int(nb_qpd[p]), q_bytes, offset
+        offset += _align(q_bytes)
+    piece_arrays = HostArrays(arrays.keep, src, nbytes, dst)
+    local = HostTables(groups=tables.groups, masks=tables.masks, pubs=k1, labels=tables.labels,
+                       lookup_start=tables.lookup_start, lookup=tables.lookup, coeffs=tables.coeffs, n_obs=n_obs,
+                       n_tallies=tables.n_tallies, data_bytes=max(offset, _ALIGN))
+    with _staging_lock(torch.cuda.current_device()):
+        if local.data_bytes <= _SIMPLE_BYTES:
+            data = _stage_simple(local, piece_arrays)
+        else:
+            stager = _BlockStager()
+            try:
+                stager.rebase([stager(src, nbytes, dst, local.data_bytes)])
+            finally:
+                stager.finish(raise_errors=False)
+            if stager.error is not None:
+                raise stager.error
+            data = stager
+    batch = DeviceBatch(tables, data, flags=flags, k1_pubs=k1)
+    batch.keepalive = arrays.keep
+    return batch
+
+
+def _label_shapes(result, n: int):
+    """Walk PUBs 0..n-1 of one label; returns the tuple ``_collect_label`` returns."""
+    return _collect_label(result, 0, n)
+
+
+def plan_sharding(results_by_label: list, collections: list, n_coeffs: int, rank: int, world: int,
+                  *, allow_tally_mode: bool = True):
+    """Decide how a call is cut over ``world`` ranks.  Deterministic: every rank reaches the same decision from the
+    same inputs (integer arithmetic on shapes every rank can see)."""
+    from . import distributed as D
+
+    if world <= 1:
+        return D.Sharding("coefficients", 0, 1, 0, n_coeffs)
+    lo, hi = D.coefficient_slice(n_coeffs, rank, world)
+    plain = D.Sharding("coefficients", rank, world, lo, hi)
+    if any(isinstance(r, D.ShardedResult) for r in results_by_label) or n_coeffs == 0:
+        return plain  # every rank holds its own equal-count shard: nothing to balance, nothing to look at
+    groups = [len(c.groups) for c in collections]
+    n_pubs = n_coeffs * sum(groups)
+    if n_pubs > D.FULL_WALK_PUBS:
+        # look at a sample of every label first: equal shapes -> equal-count slices are byte balanced
+        uniform = True
+        for result, G in zip(results_by_label, groups):
+            shapes = set()
+            for g in range(G):
+                for i in np.unique(np.linspace(0, n_coeffs - 1, num=min(n_coeffs, 32), dtype=np.int64)).tolist():
+                    _, _, _, s, nbo, nbq = _collect_label(result, i * G + g, i * G + g + 1)
+                    shapes.add((g, int(s[0]), int(nbo[0]), int(nbq[0])))
+            uniform = uniform and len(shapes) == G
+        if uniform:
+            return plain
+    collected = {}
+    weights = np.zeros(n_coeffs, dtype=np.int64)
+    for li, (result, G) in enumerate(zip(results_by_label, groups)):
+        walked = _label_shapes(result, n_coeffs * G)
+        collected[li] = walked
+        _, _, _, shots, nbo, nbq = walked
+        weights += (shots * (nbo + nbq)).reshape(n_coeffs, G).sum(axis=1)
+    slices = D.balanced_slices(weights, world)
+    imb = D.imbalance(weights, slices)
+    n_tallies = n_coeffs * sum(len(g.pauli_bitmasks) for c in collections for g in c.groups)
+    if allow_tally_mode and (n_coeffs < world or imb > D.MAX_IMBALANCE) and n_tallies <= D.MAX_TALLY_TABLE:
+        return D.Sharding("tallies", rank, world, 0, n_coeffs, "bytes", 1.0, collected)
+    lo, hi = slices[rank]
+    return D.Sharding("coefficients", rank, world, lo, hi, "bytes", imb, collected)
 
 
 last_stage_trace: dict = {}  # timing of the most recent stage_v2 call (diagnostics only)

@@ -27,19 +27,15 @@ code produced.  Floats are stored with ``float.hex`` so fixtures are bit-exact.
 from __future__ import annotations
 
 import base64
-import importlib.util
 import json
 import sys
-import types
-from collections import defaultdict
-from collections.abc import Hashable, Mapping, Sequence
+from collections.abc import Mapping
 from pathlib import Path
 
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
-REF = Path("/root/reference/qiskit_addon_cutting")
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
@@ -47,43 +43,7 @@ from qiskit_addon_cutting_b200 import containers as C  # noqa: E402
 import _cases  # noqa: E402
 
 
-def load_reference() -> dict:
-    qi = types.ModuleType("qiskit.quantum_info")
-    qi.Pauli, qi.PauliList = C.Pauli, C.PauliList
-    qp = types.ModuleType("qiskit.primitives")
-    qp.SamplerResult, qp.PrimitiveResult = C.SamplerResult, C.PrimitiveResult
-    qk = types.ModuleType("qiskit")
-    qk.quantum_info, qk.primitives = qi, qp
-    sys.modules.update({"qiskit": qk, "qiskit.quantum_info": qi, "qiskit.primitives": qp})
-
-    spec = importlib.util.spec_from_file_location("_ref_observable_grouping", REF / "utils" / "observable_grouping.py")
-    og = importlib.util.module_from_spec(spec)
-    sys.modules[spec.name] = og  # dataclasses resolves annotations through sys.modules
-    spec.loader.exec_module(og)
-
-    def lines(path: Path, lo: int, hi: int) -> str:
-        return "".join(path.read_text().splitlines(keepends=True)[lo - 1 : hi])
-
-    ns = {
-        "np": np,
-        "Mapping": Mapping,
-        "Sequence": Sequence,
-        "Hashable": Hashable,
-        "defaultdict": defaultdict,
-        "PauliList": C.PauliList,
-        "SamplerResult": C.SamplerResult,
-        "PrimitiveResult": C.PrimitiveResult,
-        "WeightType": C.WeightType,
-        "CommutingObservableGroup": og.CommutingObservableGroup,
-        "ObservableCollection": og.ObservableCollection,
-        "observables_restricted_to_subsystem": og.observables_restricted_to_subsystem,
-    }
-    future = "from __future__ import annotations\n"
-    exec(compile(future + lines(REF / "cutting_decomposition.py", 237, 260), "ref:decompose_observables", "exec"), ns)
-    exec(compile(future + lines(REF / "cutting_experiments.py", 362, 370), "ref:_get_pauli_indices", "exec"), ns)
-    exec(compile(future + lines(REF / "cutting_reconstruction.py", 31, 232), "ref:cutting_reconstruction", "exec"), ns)
-    ns["_og"] = og
-    return ns
+from oracle.ref_loader import load_reference, load_reference_terms  # noqa: E402
 
 
 def b64(a: np.ndarray) -> str:
@@ -139,17 +99,6 @@ def dump_case(name: str, ref: dict, results, coefficients, observables) -> dict:
         "labels": labels,
         "reference_expvals": [float(v).hex() for v in expvals],
     }
-
-
-def load_reference_terms():
-    """The reference's ``utils/observable_terms.py``, imported unmodified against the stand-ins."""
-    qi = sys.modules["qiskit.quantum_info"]
-    qi.SparsePauliOp = C.SparsePauliOp
-    spec = importlib.util.spec_from_file_location("_ref_observable_terms", REF / "utils" / "observable_terms.py")
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[spec.name] = mod
-    spec.loader.exec_module(mod)
-    return mod
 
 
 def dump_observable(o) -> dict:

@@ -262,43 +262,134 @@ def build_tables(w: Workload, rank: int = 0, world: int = 1):
     return builder.tables(np.concatenate(chunks), coeffs, tally, max(offset, _ALIGN))
 
 
-def device_data(tables, seed: int):
-    """Uniformly random shot bytes resident in HBM (every bit of every row random, pad bits included)."""
+def _pub_families(tables):
+    """PUB rows in arithmetic progression: yields (first_row, count, row_stride) per (label, group) so that whole families
+    of equally shaped PUBs can be addressed as one strided device view."""
+    labels = tables.labels
+    ends = [int(lab["pub_base"]) for lab in labels[1:]] + [len(tables.pubs)]
+    for lab, end in zip(labels, ends):
+        G, base = int(lab["num_groups"]), int(lab["pub_base"])
+        if G == 0 or end <= base:
+            continue
+        for g in range(G):
+            yield base + g, (end - base) // G, G
+
+
+def device_data(tables, seed: int, *, biased: bool = True, chunk_bytes: int = 1 << 30):
+    """Seeded synthetic shot bytes resident in HBM.
+
+    ``biased`` (default): every bit of every row is Bernoulli(p) with a per-(PUB, bit) bias
+    p in {0.25, 0.75}, so single-qubit expectation values are +-0.5 and the reference's sequential fp64 rounding noise
+    is exercised; of each PUB's qpd row only a random ~quarter of the bits is ever set (the cut measurements its basis
+    elements contain), the other bits are constant 0 like the registers a sampler returns.  Pad bits of the
+    observable rows stay random on purpose (masks must ignore them).  ``biased=False``: uniform bytes.
+    """
     import torch
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed)
     n = tables.data_bytes + 128  # QCUT_DATA_SLACK: readable slack after the last matrix
-    words = (n + 7) // 8
-    data = torch.randint(-(2**63), 2**63 - 1, (words,), dtype=torch.int64, device="cuda", generator=gen)
-    return data.view(torch.uint8)[:n]
+
+    def rand_bytes(count):
+        words = (count + 7) // 8
+        return torch.randint(-(2**63), 2**63 - 1, (words,), dtype=torch.int64, device="cuda", generator=gen).view(torch.uint8)[:count]
+
+    data = rand_bytes(n)
+    if not biased or len(tables.pubs) == 0:
+        return data
+    pubs = tables.pubs
+    nb_of = tables.groups["nb_obs"][pubs["group"]].astype(np.int64)
+    for first, count, stride in _pub_families(tables):
+        rows = pubs[first: first + count * stride: stride]
+        S, nb, nbq = int(rows["shots"][0]), int(nb_of[first]), int(rows["nb_qpd"][0])
+        uniform = count == 1 or (
+            np.all(rows["shots"] == S) and np.all(rows["nb_qpd"] == nbq)
+            and np.all(np.diff(rows["obs_offset"].astype(np.int64)) == int(rows["obs_offset"][1]) - int(rows["obs_offset"][0]))
+            and np.all(np.diff(rows["qpd_offset"].astype(np.int64)) == int(rows["qpd_offset"][1]) - int(rows["qpd_offset"][0])))
+        if not uniform or S == 0:
+            raise ValueError("device_data(biased=True) expects equally shaped PUBs per (label, group)")
+        step = int(rows["obs_offset"][1]) - int(rows["obs_offset"][0]) if count > 1 else S * nb
+        for which, width in (("obs_offset", nb), ("qpd_offset", nbq)):
+            per = max(1, chunk_bytes // max(1, S * width))
+            for c0 in range(0, count, per):
+                c1 = min(count, c0 + per)
+                view = torch.as_strided(data, (c1 - c0, S, width), (step, width, 1), int(rows[which][c0]))
+                r2 = rand_bytes((c1 - c0) * S * width).view(c1 - c0, S, width)
+                sel = rand_bytes((c1 - c0) * width).view(c1 - c0, 1, width)
+                # bit = (r1 & (r2 | sel)) | (r2 & sel): sel = 0 -> r1 & r2 (p = 1/4), sel = 1 -> r1 | r2 (p = 3/4)
+                view.bitwise_and_(r2 | sel)
+                view.bitwise_or_(r2.bitwise_and_(sel))
+                if which == "qpd_offset":
+                    active = rand_bytes((c1 - c0) * width).view(c1 - c0, 1, width) & rand_bytes((c1 - c0) * width).view(c1 - c0, 1, width)
+                    view.bitwise_and_(active)
+                del r2
+    return data
 
 
-def host_results(w: Workload, tables, host_bytes: np.ndarray) -> dict:
-    """Per-label ``PrimitiveResult`` whose BitArrays are views into ``host_bytes`` (the staged layout).
+def slice_tables(tables, c_lo: int, c_hi: int, coeffs: np.ndarray | None = None):
+    """HostTables of coefficient tuples ``[c_lo, c_hi)`` of every subsystem, addressing the SAME staged buffer
+    (strong-scaling legs: rank r of N works on C/N of the resident tuples)."""
+    import dataclasses
 
-    Only used to feed the public API / the CPU baseline with exactly the bytes the kernels saw.
+    labels = tables.labels.copy()
+    ends = [int(lab["pub_base"]) for lab in tables.labels[1:]] + [len(tables.pubs)]
+    chunks, base, tally = [], 0, 0
+    for li, (lab, end) in enumerate(zip(tables.labels, ends)):
+        G, pb = int(lab["num_groups"]), int(lab["pub_base"])
+        rows = tables.pubs[pb + c_lo * G: min(pb + c_hi * G, end)].copy()
+        T = tables.groups["n_terms"][rows["group"]].astype(np.int64)
+        rows["tally_offset"] = tally + np.concatenate([[0], np.cumsum(T)[:-1]]) if len(rows) else 0
+        tally += int(T.sum())
+        labels[li]["pub_base"] = base
+        base += len(rows)
+        chunks.append(rows)
+    sub = tables.coeffs[c_lo:c_hi] if coeffs is None else np.ascontiguousarray(coeffs, dtype=np.float64)
+    return dataclasses.replace(tables, pubs=np.concatenate(chunks), labels=labels, coeffs=sub, n_tallies=tally)
+
+
+def host_results(w: Workload, tables, fetch, *, world: int = 1, rank: int = 0) -> dict:
+    """Per-label ``PrimitiveResult`` holding exactly the bytes the kernels saw, every ``BitArray`` in an allocation of
+    its own (as a sampler returns them -- 2 x #PUB separate NumPy arrays, not views of one buffer).
+
+    ``fetch(lo, hi)`` returns bytes ``[lo, hi)`` of the staged layout as a host array.  With ``world > 1`` the
+    result describes the GLOBAL problem (``world * n_coeffs`` tuples) of which this process holds tuples
+    ``[rank * n_coeffs, (rank + 1) * n_coeffs)``; the other entries are absent (``distributed.ShardedResult``).
     """
     colls = w.collections()
     out = {}
-    p = 0
     nbq = (w.qpd_bits + 7) // 8
-    for label, coll in zip(w.observables, colls):
+    ends = [int(lab["pub_base"]) for lab in tables.labels[1:]] + [len(tables.pubs)]
+    for label, coll, lab, end in zip(w.observables, colls, tables.labels, ends):
+        base = int(lab["pub_base"])
         G = len(coll.groups)
         pubs = []
-        for _ in range(w.n_coeffs):
-            for g in range(G):
+        block = 4096
+        for b0 in range(base, end, block):
+            b1 = min(end, b0 + block)
+            lo = int(tables.pubs["obs_offset"][b0])
+            last = tables.pubs[b1 - 1]
+            hi = int(last["qpd_offset"]) + int(last["shots"]) * nbq
+            chunk = fetch(lo, hi)
+            for p in range(b0, b1):
                 pub = tables.pubs[p]
                 nb = int(tables.groups[pub["group"]]["nb_obs"])
                 S = int(pub["shots"])
-                o = host_bytes[int(pub["obs_offset"]) : int(pub["obs_offset"]) + S * nb].reshape(S, nb)
-                q = host_bytes[int(pub["qpd_offset"]) : int(pub["qpd_offset"]) + S * nbq].reshape(S, nbq)
-                pubs.append(
-                    PubResult(DataBin(observable_measurements=BitArray(o, nb * 8), qpd_measurements=BitArray(q, nbq * 8)))
-                )
-                p += 1
-        out[label] = PrimitiveResult(pubs)
+                oo, qo = int(pub["obs_offset"]) - lo, int(pub["qpd_offset"]) - lo
+                o = chunk[oo: oo + S * nb].reshape(S, nb).copy()
+                q = chunk[qo: qo + S * nbq].reshape(S, nbq).copy()
+                pubs.append(PubResult(DataBin(observable_measurements=BitArray(o, nb * 8), qpd_measurements=BitArray(q, nbq * 8))))
+        if world > 1:
+            from qiskit_addon_cutting_b200.distributed import ShardedResult
+
+            out[label] = ShardedResult(world * w.n_coeffs * G, rank * w.n_coeffs * G, pubs)
+        else:
+            out[label] = PrimitiveResult(pubs)
     return out
+
+
+def device_fetch(data):
+    """``fetch`` for :func:`host_results` reading from the resident device buffer."""
+    return lambda lo, hi: data[lo:hi].cpu().numpy()
 
 
 def coefficient_pairs(coeffs: np.ndarray) -> list:

@@ -157,8 +157,11 @@ class Workload:
 
     def coefficients(self, rank: int = 0, world: int = 1) -> np.ndarray:
         """Global coefficient list (C * world entries, sum |c| = kappa); rank r owns slice r."""
+        return self.coefficients_global(self.n_coeffs * world)
+
+    def coefficients_global(self, n: int) -> np.ndarray:
+        """``n`` seeded coefficients with sum |c| = kappa, sorted by weight like the reference's sampled tuples."""
         rng = np.random.default_rng(self.seed + 7)
-        n = self.n_coeffs * world
         counts = rng.multinomial(max(10 * n, 1000), np.ones(n) / n).astype(np.float64)
         counts = -np.sort(-counts)  # generate_cutting_experiments sorts samples by frequency (cutting_experiments.py:135)
         signs = rng.choice([-1.0, 1.0], size=n)
@@ -196,7 +199,7 @@ def get_workload(name: str, scale: float = 1.0) -> Workload:
                         observables_wide(303, True), c(36), 1_000_000, 2, 9.0, 303)
     if name == "cfg3_wide_local":
         return Workload(name, "configs[2] 2x64 qubits, 10^6 shots, 100-term observable (weight 1-4 XYZ, many groups)",
-                        observables_wide(304, False), c(4), 1_000_000, 2, 9.0, 304)
+                        observables_wide(304, False), c(36), 1_000_000, 2, 9.0, 304)
     if name == "cfg4_heavy_hex":
         return Workload(name, "configs[3] 127-qubit heavy-hex in 2 halves, 8 cut CNOTs, ~10^5 sampled tuples",
                         observables_heavy_hex(), c(97_000), 8192, 8, 6561.0, 404)
@@ -223,8 +226,31 @@ WORKLOADS = ["cfg1_tutorial", "cfg2_wire", "cfg3_wide_dense", "cfg3_wide_local",
 # ------------------------------------------------------------------------------------------------
 # Tables and data
 # ------------------------------------------------------------------------------------------------
-def build_tables(w: Workload, rank: int = 0, world: int = 1):
-    """HostTables of one rank's share, built without walking Python PUB objects (vectorised)."""
+def shard(w: Workload, rank: int, world: int, scaling: str = "weak"):
+    """One rank's share of the global problem: ``(local workload, global coefficient vector, (lo, hi))``.
+
+    weak: every rank holds ``w.n_coeffs`` tuples of a global list of ``world * w.n_coeffs``; strong: the global list has
+    ``w.n_coeffs`` tuples and rank r holds the r-th equal-count slice (what ``reconstruct_expectation_values`` with a
+    process group assigns to it)."""
+    import copy
+
+    from qiskit_addon_cutting_b200.distributed import coefficient_slice
+
+    if scaling == "weak" or world == 1:
+        total = w.n_coeffs * world
+        lo, hi = rank * w.n_coeffs, (rank + 1) * w.n_coeffs
+        local = w
+    else:
+        total = w.n_coeffs
+        lo, hi = coefficient_slice(total, rank, world)
+        local = copy.copy(w)
+        local.n_coeffs = hi - lo
+    return local, w.coefficients_global(total), (lo, hi)
+
+
+def build_tables(w: Workload, rank: int = 0, world: int = 1, *, coeffs: np.ndarray | None = None):
+    """HostTables of one rank's share, built without walking Python PUB objects (vectorised).  ``coeffs``: this
+    rank's ``w.n_coeffs`` coefficients (default: slice ``rank`` of the weak-scaling global list)."""
     from qiskit_addon_cutting_b200 import engine
     from qiskit_addon_cutting_b200._lib import PUB_DTYPE
 
@@ -257,8 +283,10 @@ def build_tables(w: Workload, rank: int = 0, world: int = 1):
         tally += int(T[g_idx].sum())
         n_pubs += len(pubs)
         chunks.append(pubs)
-    lo = rank * w.n_coeffs
-    coeffs = w.coefficients(rank, world)[lo : lo + w.n_coeffs]
+    if coeffs is None:
+        lo = rank * w.n_coeffs
+        coeffs = w.coefficients(rank, world)[lo : lo + w.n_coeffs]
+    assert len(coeffs) == w.n_coeffs
     return builder.tables(np.concatenate(chunks), coeffs, tally, max(offset, _ALIGN))
 
 
@@ -347,13 +375,15 @@ def slice_tables(tables, c_lo: int, c_hi: int, coeffs: np.ndarray | None = None)
     return dataclasses.replace(tables, pubs=np.concatenate(chunks), labels=labels, coeffs=sub, n_tallies=tally)
 
 
-def host_results(w: Workload, tables, fetch, *, world: int = 1, rank: int = 0) -> dict:
+def host_results(w: Workload, tables, fetch, *, total_coeffs: int | None = None, first_coeff: int = 0,
+                 max_coeffs: int | None = None, max_shots: int | None = None) -> dict:
     """Per-label ``PrimitiveResult`` holding exactly the bytes the kernels saw, every ``BitArray`` in an allocation of
     its own (as a sampler returns them -- 2 x #PUB separate NumPy arrays, not views of one buffer).
 
-    ``fetch(lo, hi)`` returns bytes ``[lo, hi)`` of the staged layout as a host array.  With ``world > 1`` the
-    result describes the GLOBAL problem (``world * n_coeffs`` tuples) of which this process holds tuples
-    ``[rank * n_coeffs, (rank + 1) * n_coeffs)``; the other entries are absent (``distributed.ShardedResult``).
+    ``fetch(lo, hi)`` returns bytes ``[lo, hi)`` of the staged layout as a host array.  With ``total_coeffs`` the
+    result describes a GLOBAL problem of that many tuples of which this process holds tuples ``first_coeff ..
+    first_coeff + n_coeffs - 1``; the other entries are absent (``distributed.ShardedResult``).  ``max_coeffs`` /
+    ``max_shots`` cut a sub-problem out (first tuples, first shots of every PUB) for the CPU legs.
     """
     colls = w.collections()
     out = {}
@@ -362,6 +392,8 @@ def host_results(w: Workload, tables, fetch, *, world: int = 1, rank: int = 0) -
     for label, coll, lab, end in zip(w.observables, colls, tables.labels, ends):
         base = int(lab["pub_base"])
         G = len(coll.groups)
+        if max_coeffs is not None:
+            end = min(end, base + max_coeffs * G)
         pubs = []
         block = 4096
         for b0 in range(base, end, block):
@@ -373,15 +405,15 @@ def host_results(w: Workload, tables, fetch, *, world: int = 1, rank: int = 0) -
             for p in range(b0, b1):
                 pub = tables.pubs[p]
                 nb = int(tables.groups[pub["group"]]["nb_obs"])
-                S = int(pub["shots"])
+                S = int(pub["shots"]) if max_shots is None else min(int(pub["shots"]), max_shots)
                 oo, qo = int(pub["obs_offset"]) - lo, int(pub["qpd_offset"]) - lo
                 o = chunk[oo: oo + S * nb].reshape(S, nb).copy()
                 q = chunk[qo: qo + S * nbq].reshape(S, nbq).copy()
                 pubs.append(PubResult(DataBin(observable_measurements=BitArray(o, nb * 8), qpd_measurements=BitArray(q, nbq * 8))))
-        if world > 1:
+        if total_coeffs is not None and total_coeffs != len(pubs) // max(G, 1):
             from qiskit_addon_cutting_b200.distributed import ShardedResult
 
-            out[label] = ShardedResult(world * w.n_coeffs * G, rank * w.n_coeffs * G, pubs)
+            out[label] = ShardedResult(total_coeffs * G, first_coeff * G, pubs)
         else:
             out[label] = PrimitiveResult(pubs)
     return out

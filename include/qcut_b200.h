@@ -192,6 +192,24 @@ int qcut_recombine_launch(const double* d_term_expvals, int expvals_complex,
                           const uint32_t* d_row_start, const uint32_t* d_term_index,
                           const double* d_coeffs, int n_rows, double* d_out, void* stream);
 
+/* ---- PUB de-duplication at ingest ----------------------------------
+ * The reference emits one subexperiment per (sample, group) and label even when that label's own map
+ * ids repeat (cutting_experiments.py:146-157, docs/explanation/index.rst:188), so a caller who runs each
+ * distinct circuit once hands the same BitArray buffers over many times.  A PUB whose six attributes
+ * (observable buffer address, qpd buffer address, shots, row widths, group variant) equal an earlier
+ * PUB's has the same bytes under the same masks: it is neither staged nor tallied again.  Contents are
+ * never hashed.  The finder keeps its hash table across the blocks of one call.
+ * qcut_dedup_block: for PUBs base .. base+n-1 writes rep[j] = global index of the first PUB with the
+ * same attributes (base+j itself when there is none, always for PUBs without shots); returns the
+ * number of duplicates in the block, or -1 on a bad argument. */
+typedef struct qcut_dedup qcut_dedup;
+int qcut_dedup_create(qcut_dedup** out);
+void qcut_dedup_destroy(qcut_dedup* finder);
+void qcut_dedup_clear(qcut_dedup* finder); /* forget every PUB, keep the memory (a finder is reused call after call) */
+int64_t qcut_dedup_block(qcut_dedup* finder, int64_t base, const uint64_t* obs_ptr, const uint64_t* qpd_ptr,
+                         const int64_t* shots, const int64_t* nb_obs, const int64_t* nb_qpd,
+                         const uint32_t* variant, int64_t n, int64_t* rep);
+
 /* ---- host staging: gather many borrowed BitArray buffers into one pinned buffer ---------------
  * Copies n_arrays host buffers (h_src[i], h_bytes[i] bytes) to h_dst + h_dst_offset[i] with
  * n_threads worker threads (0 = hardware concurrency).  Pure host code; used on the end-to-end

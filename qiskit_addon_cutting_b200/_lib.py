@@ -96,6 +96,10 @@ SIGNATURES = {
     "qcut_quasi_launch": (_INT, [_VP, _I64, _VP, _VP, _VP, _VP, _INT, _VP, _INT, _VP, _VP, _VP]),
     "qcut_reduce_expvals_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
     "qcut_recombine_launch": (_INT, [_VP, _INT, _VP, _VP, _VP, _INT, _VP, _VP]),
+    "qcut_dedup_create": (_INT, [C.POINTER(_VP)]),
+    "qcut_dedup_destroy": (None, [_VP]),
+    "qcut_dedup_clear": (None, [_VP]),
+    "qcut_dedup_block": (_I64, [_VP, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "qcut_gather_host": (_INT, [_VP, _VP, _VP, _I64, _VP, _INT]),
     "qcut_stage_h2d": (_INT, [_VP, _VP, _VP, _I64, _VP, _SZ, _VP, _INT, _VP]),
     "qcut_generate_source": (_SZ, [_VP, _INT, _VP, _SZ, _INT, C.c_char_p, _SZ]),

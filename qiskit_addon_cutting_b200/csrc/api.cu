@@ -548,6 +548,105 @@ int qcut_gather_host(const void* const* h_src, const uint64_t* h_bytes, const ui
 
 }  // extern "C"
 
+// ---- PUB de-duplication: open-addressing hash table over the six attributes of a PUB ------------------
+// The table holds (hash, index) pairs only (16 bytes per slot); the attributes of every distinct PUB are
+// appended to `keys` and compared when the hashes match.  Slots of a batch of PUBs are prefetched before
+// they are probed: at 4 x 10^5 PUBs the table is far larger than the caches.
+struct qcut_dedup {
+  struct Key { uint64_t obs, qpd; int64_t shots; uint32_t nb_obs, nb_qpd, variant, pad; int64_t index; };
+  struct Slot { uint64_t hash; int64_t key; };  // key = position in `keys`, -1 = empty
+  std::vector<Slot> table;
+  std::vector<Key> keys;
+  static uint64_t hash(const Key& k) {
+    uint64_t h = k.obs * 0x9E3779B97F4A7C15ull;
+    h ^= (k.qpd + 0xC2B2AE3D27D4EB4Full) * 0x165667B19E3779F9ull;
+    h ^= ((uint64_t)k.shots << 32 | k.variant) * 0x27D4EB2F165667C5ull;
+    h ^= ((uint64_t)k.nb_obs << 16 | k.nb_qpd) * 0x85EBCA77C2B2AE63ull;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    return h ^ (h >> 32);
+  }
+  static bool same(const Key& a, const Key& b) {
+    return a.obs == b.obs && a.qpd == b.qpd && a.shots == b.shots && a.nb_obs == b.nb_obs && a.nb_qpd == b.nb_qpd &&
+           a.variant == b.variant;
+  }
+  void reserve(size_t n_keys) {
+    size_t want = (size_t)1 << 12;
+    while (want < 2 * n_keys + 2) want <<= 1;
+    if (want <= table.size()) return;
+    std::vector<Slot> old;
+    old.swap(table);
+    table.assign(want, Slot{0, -1});
+    const size_t mask = want - 1;
+    for (const Slot& e : old) {
+      if (e.key < 0) continue;
+      size_t i = (size_t)e.hash & mask;
+      while (table[i].key >= 0) i = (i + 1) & mask;
+      table[i] = e;
+    }
+  }
+};
+
+extern "C" {
+
+int qcut_dedup_create(qcut_dedup** out) {
+  if (!out) return set_error("qcut_dedup_create: out is NULL"), QCUT_ERR_INVALID;
+  *out = new (std::nothrow) qcut_dedup();
+  return *out ? QCUT_OK : (set_error("qcut_dedup_create: out of memory"), QCUT_ERR_INVALID);
+}
+
+void qcut_dedup_destroy(qcut_dedup* finder) { delete finder; }
+
+void qcut_dedup_clear(qcut_dedup* finder) {
+  if (!finder) return;
+  finder->keys.clear();  // capacity (and the touched pages) are kept for the next call
+  std::fill(finder->table.begin(), finder->table.end(), qcut_dedup::Slot{0, -1});
+}
+
+int64_t qcut_dedup_block(qcut_dedup* finder, int64_t base, const uint64_t* obs_ptr, const uint64_t* qpd_ptr,
+                         const int64_t* shots, const int64_t* nb_obs, const int64_t* nb_qpd,
+                         const uint32_t* variant, int64_t n, int64_t* rep) {
+  if (!finder || n < 0 || (n > 0 && (!obs_ptr || !qpd_ptr || !shots || !nb_obs || !nb_qpd || !variant || !rep)))
+    return set_error("qcut_dedup_block: bad argument"), -1;
+  finder->reserve(finder->keys.size() + (size_t)n);  // no growth inside the loop
+  finder->keys.reserve(finder->keys.size() + (size_t)n);
+  const size_t mask = finder->table.size() - 1;
+  constexpr int kBatch = 16;
+  int64_t duplicates = 0;
+  for (int64_t j0 = 0; j0 < n; j0 += kBatch) {
+    const int m = (int)std::min<int64_t>(kBatch, n - j0);
+    qcut_dedup::Key key[kBatch];
+    uint64_t h[kBatch];
+    for (int b = 0; b < m; ++b) {
+      const int64_t j = j0 + b;
+      key[b] = qcut_dedup::Key{obs_ptr[j], qpd_ptr[j], shots[j], (uint32_t)nb_obs[j], (uint32_t)nb_qpd[j], variant[j], 0u, base + j};
+      h[b] = qcut_dedup::hash(key[b]);
+      __builtin_prefetch(&finder->table[(size_t)h[b] & mask]);
+    }
+    for (int b = 0; b < m; ++b) {
+      const int64_t j = j0 + b;
+      rep[j] = base + j;
+      if (shots[j] <= 0) continue;  // nothing to stage or tally anyway
+      for (size_t i = (size_t)h[b] & mask;; i = (i + 1) & mask) {
+        qcut_dedup::Slot& e = finder->table[i];
+        if (e.key < 0) {
+          e = qcut_dedup::Slot{h[b], (int64_t)finder->keys.size()};
+          finder->keys.push_back(key[b]);
+          break;
+        }
+        if (e.hash == h[b] && qcut_dedup::same(finder->keys[(size_t)e.key], key[b])) {
+          rep[j] = finder->keys[(size_t)e.key].index;
+          ++duplicates;
+          break;
+        }
+      }
+    }
+  }
+  return duplicates;
+}
+
+}  // extern "C"
+
 namespace {
 // Copy into the pinned ring.  streaming = true uses non-temporal stores: the ring is written once and
 // read once by the DMA engine, so the destination lines need not be fetched or kept in the caches.

@@ -140,10 +140,30 @@ class HostTables:
     n_obs: int
     n_tallies: int
     data_bytes: int
+    # PUB de-duplication: when some PUBs are the very same buffers as earlier ones,
+    # ``k1_pubs`` lists the distinct PUBs -- the only ones staged and tallied -- while ``pubs`` keeps one row per
+    # PUB for the product/sum kernel, duplicates carrying the offsets of their first occurrence.  None: no duplicates.
+    k1_pubs: np.ndarray | None = None
+
+    @property
+    def staged_pubs(self) -> np.ndarray:
+        """The PUBs whose bytes are staged and tallied (all of them unless duplicates were found)."""
+        return self.pubs if self.k1_pubs is None else self.k1_pubs
+
+    @property
+    def dedup(self) -> dict:
+        """How much the duplicate detection saved: PUBs / shot bytes handed over vs staged and tallied."""
+        def nbytes(pubs):
+            nb = self.groups["nb_obs"][pubs["group"]].astype(np.int64) + pubs["nb_qpd"].astype(np.int64)
+            return int((pubs["shots"].astype(np.int64) * nb).sum())
+
+        total, staged = nbytes(self.pubs), nbytes(self.staged_pubs)
+        return {"pubs": int(len(self.pubs)), "distinct_pubs": int(len(self.staged_pubs)), "shot_bytes": total,
+                "staged_shot_bytes": staged, "dedup_ratio": total / staged if staged else 1.0}
 
     @property
     def n_tiles(self) -> int:
-        return int(((self.pubs["shots"].astype(np.int64) + TILE_SHOTS - 1) // TILE_SHOTS).sum())
+        return int(((self.staged_pubs["shots"].astype(np.int64) + TILE_SHOTS - 1) // TILE_SHOTS).sum())
 
     @property
     def single_slot(self) -> bool:
@@ -158,8 +178,9 @@ class HostTables:
     @property
     def algorithmic_bytes(self) -> int:
         """Bytes K1 + K2 must move: shot rows once, tallies written and read, coeffs, out."""
-        nb = self.groups["nb_obs"][self.pubs["group"]].astype(np.int64) + self.pubs["nb_qpd"].astype(np.int64)
-        shot_bytes = int((self.pubs["shots"].astype(np.int64) * nb).sum())
+        pubs = self.staged_pubs
+        nb = self.groups["nb_obs"][pubs["group"]].astype(np.int64) + pubs["nb_qpd"].astype(np.int64)
+        shot_bytes = int((pubs["shots"].astype(np.int64) * nb).sum())
         return shot_bytes + 16 * self.n_tallies + 8 * len(self.coeffs) + 8 * self.n_obs
 
 
@@ -254,6 +275,8 @@ class DeviceBatch:
         data offsets and shot counts but the global ``tally_offset`` -- while ``tables.pubs`` stays the complete
         table the product/sum kernel reads after the tally table has been all-reduced."""
         self.tables = tables
+        if k1_pubs is None:
+            k1_pubs = tables.k1_pubs
         self.plan = get_plan(tables.groups, tables.masks, flags=flags)
         self.schedule = Schedule(self.plan, tables.pubs if k1_pubs is None else k1_pubs)
         self.data = data
@@ -408,6 +431,61 @@ class HostArrays:
         return len(self.src)
 
 
+_DEDUP = os.environ.get("QCUT_DEDUP", "1") not in ("0", "", "off")
+
+
+class _DuplicateFinder:
+    """Finds PUBs whose two ``BitArray`` buffers are the very same memory as an earlier PUB's (``qcut_dedup_*``).
+
+    The reference emits one subexperiment per (sample, group) and label even when the label's own map ids repeat
+    (``cutting_experiments.py:146-157``; ``docs/explanation/index.rst:188``), so a caller who runs each distinct
+    circuit once hands the same result object over many times.  Same addresses + same shape + same group variant =>
+    same bytes, same masks => same tallies: such a PUB is neither staged nor tallied again.  Content is never
+    hashed (two separately sampled runs of one circuit differ)."""
+
+    _idle: list = []  # finders of finished calls: their hash tables keep their (already touched) memory
+
+    @classmethod
+    def acquire(cls) -> "_DuplicateFinder":
+        try:
+            finder = cls._idle.pop()
+        except IndexError:
+            return cls()
+        _lib.load().qcut_dedup_clear(finder.handle)
+        finder.duplicates = 0
+        return finder
+
+    def release(self) -> None:
+        if len(self._idle) < 4:
+            self._idle.append(self)
+
+    def __init__(self):
+        handle = C.c_void_p()
+        check(_lib.load().qcut_dedup_create(C.byref(handle)), "qcut_dedup_create")
+        self.handle = handle
+        self.duplicates = 0
+
+    def representatives(self, base: int, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd, variant) -> np.ndarray:
+        """Global index of the first PUB with the same buffers, for every PUB of a block starting at ``base``."""
+        n = len(obs_ptr)
+        rep = np.empty(n, dtype=np.int64)
+        cols = [np.ascontiguousarray(a, dtype=t) for a, t in ((obs_ptr, np.uint64), (qpd_ptr, np.uint64), (shots, np.int64),
+                                                              (nb_obs, np.int64), (nb_qpd, np.int64), (variant, np.uint32))]
+        found = _lib.load().qcut_dedup_block(self.handle, base, *[_lib.np_ptr(a) for a in cols], n, _lib.np_ptr(rep))
+        if found < 0:
+            check(1, "qcut_dedup_block")
+        self.duplicates += int(found)
+        return rep
+
+    def __del__(self):
+        handle, self.handle = getattr(self, "handle", None), None
+        if handle:
+            try:
+                _lib.load().qcut_dedup_destroy(handle)
+            except Exception:  # interpreter shutdown
+                pass
+
+
 def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int,
                       n_obs: int, *, sink=None, block_pubs: int = 0, collected: dict | None = None) -> tuple[HostTables, HostArrays]:
     """Walk the PUBs of coefficient range ``[i_lo, i_hi)`` of every label (host only, no device).
@@ -421,6 +499,8 @@ def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndar
     builder = TableBuilder(n_obs)
     keep_all: list = []
     src_chunks, nbytes_chunks, dst_chunks, chunks, bases = [], [], [], [], []
+    finder = _DuplicateFinder.acquire() if _DEDUP else None
+    k1_chunks, rep_chunks = [], []  # distinct PUBs of every block / representative (global PUB index) of every PUB
     offset = 0
     tally_offset = 0
     n_pubs = 0
@@ -451,13 +531,28 @@ def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndar
             terms = terms_of_group[g_idx]
             if n and int(shots.max()) >= 2**31:
                 raise ValueError("A PUB with 2**31 or more shots is not supported.")
-            raw = np.empty(2 * n, dtype=np.int64)
+            pubs = np.zeros(n, dtype=PUB_DTYPE)
+            pubs["shots"] = shots
+            pubs["group"] = variant
+            pubs["nb_qpd"] = nb_qpd
+            # PUBs that are the same buffers as an earlier PUB are neither staged nor tallied again
+            rep = finder.representatives(n_pubs, obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd, variant) if finder else None
+            rep_chunks.append(rep if rep is not None else n_pubs + np.arange(n, dtype=np.int64))
+            fresh = None
+            if rep is not None and n:
+                fresh = rep == n_pubs + np.arange(n, dtype=np.int64)
+                if fresh.all():
+                    fresh = None
+            if fresh is not None:
+                obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd, terms = (a[fresh] for a in (obs_ptr, qpd_ptr, shots, nb_obs, nb_qpd, terms))
+            m = len(shots)  # distinct PUBs of the block
+            raw = np.empty(2 * m, dtype=np.int64)
             raw[0::2] = shots * nb_obs
             raw[1::2] = shots * nb_qpd
             sizes = (raw + _ALIGN - 1) // _ALIGN * _ALIGN
-            starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+            starts = np.cumsum(sizes) - sizes
             block_bytes = int(sizes.sum())
-            src = np.empty(2 * n, dtype=np.uint64)
+            src = np.empty(2 * m, dtype=np.uint64)
             src[0::2] = obs_ptr
             src[1::2] = qpd_ptr
             nbytes = raw.astype(np.uint64)
@@ -466,13 +561,10 @@ def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndar
             else:
                 base = 0
                 bases.append(sink(src, nbytes, starts.astype(np.uint64), block_bytes))
-            pubs = np.zeros(n, dtype=PUB_DTYPE)
-            pubs["obs_offset"] = base + starts[0::2]
-            pubs["qpd_offset"] = base + starts[1::2]
-            pubs["tally_offset"] = tally_offset + np.concatenate([[0], np.cumsum(terms)[:-1]])
-            pubs["shots"] = shots
-            pubs["group"] = variant
-            pubs["nb_qpd"] = nb_qpd
+            k1 = pubs if fresh is None else pubs[fresh]
+            k1["obs_offset"] = base + starts[0::2]
+            k1["qpd_offset"] = base + starts[1::2]
+            k1["tally_offset"] = tally_offset + np.cumsum(terms) - terms
             src_chunks.append(src)
             nbytes_chunks.append(nbytes)
             dst_chunks.append((base + starts).astype(np.uint64))
@@ -480,16 +572,30 @@ def build_host_tables(results_by_label: list, collections: list, coeffs: np.ndar
             tally_offset += int(terms.sum())
             n_pubs += n
             chunks.append(pubs)
+            k1_chunks.append(k1)
             keep_all.extend(keep)
     if sink is not None:
         # the blocks live in separate device allocations: make every offset relative to the lowest one
-        for pubs, delta in zip(chunks, sink.rebase(bases)):
-            pubs["obs_offset"] += np.uint64(delta)
-            pubs["qpd_offset"] += np.uint64(delta)
+        for k1, delta in zip(k1_chunks, sink.rebase(bases)):
+            k1["obs_offset"] += np.uint64(delta)
+            k1["qpd_offset"] += np.uint64(delta)
     pubs = np.concatenate(chunks) if chunks else np.zeros(0, dtype=PUB_DTYPE)
+    k1_pubs = None
+    if finder is not None and finder.duplicates:
+        # one row per PUB for the product/sum kernel: a duplicate carries the offsets of its first occurrence
+        k1_pubs = np.concatenate(k1_chunks)
+        rep_all = np.concatenate(rep_chunks)
+        fresh_all = rep_all == np.arange(len(pubs))
+        for f in ("obs_offset", "qpd_offset", "tally_offset"):
+            pubs[f][fresh_all] = k1_pubs[f]
+            pubs[f] = pubs[f][rep_all]
     cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint64)  # noqa: E731
     arrays = HostArrays(keep_all, cat(src_chunks), cat(nbytes_chunks), cat(dst_chunks))
-    return builder.tables(pubs, coeffs[i_lo:i_hi], tally_offset, max(offset, _ALIGN)), arrays
+    if finder is not None:
+        finder.release()
+    tables = builder.tables(pubs, coeffs[i_lo:i_hi], tally_offset, max(offset, _ALIGN))
+    tables.k1_pubs = k1_pubs
+    return tables, arrays
 
 
 def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_threads: int = 0) -> None:
@@ -685,7 +791,7 @@ def stage_v2_pieces(results_by_label: list, collections: list, coeffs: np.ndarra
 
     _lib.require_device()
     tables, arrays = build_host_tables(results_by_label, collections, coeffs, 0, len(coeffs), n_obs, collected=collected)
-    pubs = tables.pubs
+    pubs = tables.staged_pubs  # duplicates are neither staged nor tallied
     nb_obs = tables.groups["nb_obs"][pubs["group"]].astype(np.int64) if len(pubs) else np.zeros(0, dtype=np.int64)
     nb_qpd = pubs["nb_qpd"].astype(np.int64)
     pieces = distributed.piece_ranges(nb_obs + nb_qpd, pubs["shots"], world, TILE_SHOTS)[rank]

@@ -189,7 +189,9 @@ def test_block_staging_many_blocks(lib, monkeypatch, name):
     """Tiny staging blocks (every label cut into several device allocations): same tallies, same result."""
     results, coefficients, observables = _cases.SMALL_CASES[name]()
     monkeypatch.setattr(engine, "_BLOCK_PUBS", 2)
+    monkeypatch.setattr(engine, "_SIMPLE_PUBS", 0)  # small inputs normally take the one-copy path: force the pipeline
     batch, got, want = _device_tallies(results, coefficients, observables)
+    assert engine.last_stage_trace["path"] == "pipelined"
     assert len(batch.data.blocks) > len(observables if isinstance(observables, dict) else [0])
     assert np.array_equal(got, want)
     out = reconstruct_expectation_values(results, coefficients, observables)
@@ -221,3 +223,45 @@ def test_concurrent_calls_from_python_threads(lib):
         t.join()
     assert not errors, errors
     assert got == [want[i % len(cases)] for i in range(len(got))]
+
+
+def _with_duplicates(results, coefficients, moves):
+    out = dict(results)
+    for label, src, dst in moves:
+        G = len(out[label]) // len(coefficients)
+        pubs = list(out[label])
+        pubs[dst * G: (dst + 1) * G] = pubs[src * G: (src + 1) * G]
+        out[label] = PrimitiveResult(pubs)
+    return out
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_duplicate_pubs_are_staged_and_tallied_once(lib, monkeypatch, pipelined):
+    """SURVEY section 8f row 4 (reference cutting_experiments.py:146-157 emits repeated subexperiments): PUBs that are
+    the same buffers as an earlier PUB are detected at ingest; fewer bytes cross PCIe, tallies of the distinct PUBs are
+    bit-exact and the expectation values are bit-identical to the exact oracle on the duplicated input."""
+    results, coefficients, observables = _cases.SMALL_CASES["molecular"]()
+    dup = _with_duplicates(results, coefficients, [("S1", 0, 3), ("S2", 2, 4), ("S2", 2, 1), ("S0", 1, 2)])
+    if pipelined:
+        monkeypatch.setattr(engine, "_BLOCK_PUBS", 3)
+        monkeypatch.setattr(engine, "_SIMPLE_PUBS", 0)
+    labels = list(observables)
+    colls = [ObservableCollection(observables[label]) for label in labels]
+    coeffs = np.array([c for c, _ in coefficients], dtype=np.float64)
+    plain = engine.stage_v2([results[k] for k in labels], colls, coeffs, 0, len(coeffs), len(observables[labels[0]]))
+    batch = engine.stage_v2([dup[k] for k in labels], colls, coeffs, 0, len(coeffs), len(observables[labels[0]]))
+    assert engine.last_stage_trace["path"] == ("pipelined" if pipelined else "simple")
+    t = batch.tables
+    assert t.k1_pubs is not None and len(t.k1_pubs) < len(t.pubs) and t.data_bytes < plain.tables.data_bytes
+    assert t.dedup["dedup_ratio"] > 1.15 and plain.tables.dedup["dedup_ratio"] == 1.0
+    batch.run()
+    torch.cuda.synchronize()
+    # tallies of the distinct PUBs, in staging order, against the oracle
+    every = [x for k in labels for x in oracle.all_tallies(dup, coefficients, observables)[k]]
+    first = sorted({int(o) for o in t.pubs["tally_offset"]})
+    want = np.concatenate([every[int(np.flatnonzero(t.pubs["tally_offset"] == o)[0])] for o in first])
+    assert np.array_equal(batch.tallies.cpu().numpy()[: t.n_tallies], want)
+    got = reconstruct_expectation_values(dup, coefficients, observables)
+    assert _hex(got) == _hex(oracle.reconstruct_exact(dup, coefficients, observables))
+    monkeypatch.setattr(engine, "_DEDUP", False)
+    assert _hex(got) == _hex(reconstruct_expectation_values(dup, coefficients, observables))

@@ -442,7 +442,8 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
                "host_buffers": f"{2 * len(tables.pubs)} separate NumPy allocations per rank (one per BitArray)",
                "api": "reconstruct_expectation_values(results, coefficients, observables"
                       + (", process_group=WORLD): sharded public API + NCCL all-reduce" if world > 1 else ")"),
-               "staging_path": engine.last_stage_trace.get("path")}
+               "staging_path": engine.last_stage_trace.get("path"),
+               "dedup_ratio": engine.last_stage_trace.get("dedup", {}).get("dedup_ratio")}
         # same bytes, same path: the API result must equal the resident-data result
         if world == 1:
             assert np.array_equal(np.array(got), resident_out), "e2e result differs from resident result"
@@ -466,6 +467,49 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
     del batch, data
     torch.cuda.empty_cache()
     return line
+
+
+def measure_dedup(args) -> dict:
+    """SURVEY section 8f row 4 on a wire-cutting shape: cfg2 (3 subsystems in a chain, 2 cut wires with 8 basis elements
+    each).  The circuit of an end subsystem depends on ONE cut's map id, that of the middle subsystem on both, so of
+    the 512 sampled tuples only 8 / 64 / 8 subexperiment sets are distinct per subsystem -- the reference still lists
+    one per tuple (cutting_experiments.py:146-157).  A caller who runs each distinct circuit once passes the same
+    PubResult objects many times; the engine stages and tallies each distinct PUB once."""
+    import torch
+
+    import workloads as W
+    from qiskit_addon_cutting_b200 import engine, reconstruct_expectation_values
+    from qiskit_addon_cutting_b200.containers import PrimitiveResult
+
+    w = W.get_workload("cfg2_wire", 1.0)
+    tables = W.build_tables(w)
+    data = W.device_data(tables, w.seed * 1000, biased=not args.uniform_data)
+    results = W.host_results(w, tables, W.device_fetch(data))
+    C = w.n_coeffs
+    shared = {}
+    for (label, res), distinct in zip(results.items(), (8, 64, 8)):
+        G = len(res) // C
+        pubs = list(res)
+        shared[label] = PrimitiveResult([pubs[((i * 8 // C) if distinct == 8 else (i * 64 // C)) % distinct * G + g]
+                                         for i in range(C) for g in range(G)])
+    pairs = W.coefficient_pairs(tables.coeffs)
+    out = {}
+    for name, flag in (("with_dedup", True), ("without_dedup", False)):
+        engine._DEDUP = flag
+        got = reconstruct_expectation_values(shared, pairs, w.observables)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(10):
+            got = reconstruct_expectation_values(shared, pairs, w.observables)
+        ms = 1e2 * (time.perf_counter() - t)
+        d = engine.last_stage_trace["dedup"]
+        out[name] = {"ms_per_call": ms, "h2d_shot_bytes": d["staged_shot_bytes"], "pubs_tallied": d["distinct_pubs"],
+                     "result": [float(v).hex() for v in got]}
+    engine._DEDUP = True
+    same = out["with_dedup"].pop("result") == out["without_dedup"].pop("result")
+    return {"workload": "cfg2_wire with shared result objects (8/64/8 distinct subexperiment sets for 512 tuples)",
+            "pubs": int(len(tables.pubs)), "dedup_ratio": out["without_dedup"]["h2d_shot_bytes"] / out["with_dedup"]["h2d_shot_bytes"],
+            "results_bit_identical": bool(same), **out}
 
 
 def ours_arm(args):
@@ -513,6 +557,10 @@ def ours_arm(args):
             rec["wall_s"] = time.perf_counter() - t0
             per.append(rec)
         line["per_config"] = per
+        try:
+            line["dedup"] = measure_dedup(args)
+        except Exception as exc:
+            line["dedup"] = {"error": repr(exc)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

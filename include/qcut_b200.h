@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QCUT_ABI_VERSION 3
+#define QCUT_ABI_VERSION 4
 /* Shots per scheduling tile (one warp processes one tile of one PUB at a time). */
 #define QCUT_TILE_SHOTS 4096
 /* Widest observable row (bytes) the kernels accept: 64 bytes = 512 measured qubits per group. */
@@ -151,15 +151,29 @@ int qcut_tally_launch(const qcut_plan* plan, const qcut_schedule* schedule, cons
  * with the expectation of PUB (label, i, g) taken as tally/shots (one correctly rounded fp64
  * division).  Deterministic: fixed partition of i, fixed-order combination; for n_coeffs <= 1024 the
  * summation order is exactly the reference's.  d_workspace must hold
- * qcut_reduce_workspace_bytes(n_coeffs, n_obs) bytes.  single_slot != 0 asserts that every
- * observable has exactly one lookup slot in every subsystem (what Qiskit's grouping yields): the
- * kernels then run straight-line code specialised for 1..4 subsystems; 0 selects the general form. */
+ * qcut_reduce_workspace_bytes(n_coeffs, n_obs) bytes.  `flags`: QCUT_REDUCE_SINGLE_SLOT asserts that
+ * every observable has exactly one lookup slot in every subsystem (what Qiskit's grouping yields): the
+ * kernels then run straight-line code specialised for 1..4 subsystems, otherwise the general form;
+ * QCUT_REDUCE_SEQUENTIAL sums the tuples in strictly ascending order whatever n_coeffs is (the
+ * reference's `expvals += coeff[0] * current_expvals` order; one CTA column walks all tuples). */
+#define QCUT_REDUCE_SINGLE_SLOT 1
+#define QCUT_REDUCE_SEQUENTIAL 2
 size_t qcut_reduce_workspace_bytes(int64_t n_coeffs, int n_obs);
 int qcut_reduce_launch(const int64_t* d_tallies, const qcut_pub_desc* d_pubs,
                        const qcut_label_desc* d_labels, int n_labels,
                        const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                        const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                       void* d_workspace, int single_slot, void* stream);
+                       void* d_workspace, int flags, void* stream);
+
+/* ---- K1, reference rounding (opt-in): per-(PUB, term) expectation values accumulated exactly like the
+ * reference does -- subsystem_expvals[k] += (1 / shots) * sign, shot by shot, in fp64
+ * (cutting_reconstruction.py:155-161) -- so d_expvals[pub.tally_offset + t] is BIT-IDENTICAL to the
+ * reference's value, including its rounding noise (up to ~6e-12 from tally / shots at 10^6 shots).
+ * One thread walks the chain of one (PUB, term) in shot order; feed the result to
+ * qcut_reduce_expvals_launch with QCUT_REDUCE_SEQUENTIAL for bit-identical final values.  Reads the
+ * PUB table of `schedule`; about an order of magnitude slower than qcut_tally_launch. */
+int qcut_expvals_literal_launch(const qcut_plan* plan, const qcut_schedule* schedule, const uint8_t* d_data,
+                                double* d_expvals, int64_t n_expvals, void* stream);
 
 /* ---- SamplerV1 quasi-distributions (reference cutting_reconstruction.py:143-149,173-193) -------
  * For PUB p, outcomes [d_dist_start[p], d_dist_start[p+1]) hold (obs bits, qpd bits, weight):
@@ -177,7 +191,7 @@ int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_p
                                const qcut_label_desc* d_labels, int n_labels,
                                const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                                const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                               void* d_workspace, int single_slot, void* stream);
+                               void* d_workspace, int flags, void* stream);
 
 /* ---- term recombination (reference utils/observable_terms.py:60-90) ------------------------------
  * The step right after the path: the expectation value of every observable (SparsePauliOp) is

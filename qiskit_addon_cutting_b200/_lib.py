@@ -20,7 +20,8 @@ LIB_PATH = PACKAGE_DIR / "libqcut_b200.so"
 TILE_SHOTS = 4096
 MAX_OBS_BYTES = 64
 DATA_SLACK = 128  # readable bytes required after the last matrix (QCUT_DATA_SLACK)
-ABI_VERSION = 3
+ABI_VERSION = 4
+REDUCE_SINGLE_SLOT, REDUCE_SEQUENTIAL = 1, 2
 PLAN_NO_JIT = 1
 PLAN_GENERIC_ONLY = 2
 PLAN_STAGED = 4
@@ -93,6 +94,7 @@ SIGNATURES = {
     "qcut_tally_launch": (_INT, [_VP, _VP, _VP, _VP, _I64, _VP, C.POINTER(_INT)]),
     "qcut_reduce_workspace_bytes": (_SZ, [_I64, _INT]),
     "qcut_reduce_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
+    "qcut_expvals_literal_launch": (_INT, [_VP, _VP, _VP, _VP, _I64, _VP]),
     "qcut_quasi_launch": (_INT, [_VP, _I64, _VP, _VP, _VP, _VP, _INT, _VP, _INT, _VP, _VP, _VP]),
     "qcut_reduce_expvals_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
     "qcut_recombine_launch": (_INT, [_VP, _INT, _VP, _VP, _VP, _INT, _VP, _VP]),

@@ -50,8 +50,9 @@ int jit_build(qcut_plan* plan, bool load);
 void jit_release(qcut_plan* plan);
 template <typename TallyT>
 int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, int, const uint32_t*,
-                  const qcut_slot*, const double*, int64_t, int, double*, void*, bool, cudaStream_t);
+                  const qcut_slot*, const double*, int64_t, int, double*, void*, bool, bool, cudaStream_t);
 size_t reduce_workspace_bytes(int64_t, int);
+int launch_literal(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, int64_t, double*, cudaStream_t);
 int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const uint64_t*, const int64_t*,
                  const uint64_t*, int, const uint64_t*, int, const double*, double*, cudaStream_t);
 int launch_recombine(const double*, bool, const uint32_t*, const uint32_t*, const double*, int, double*, cudaStream_t);
@@ -481,21 +482,36 @@ size_t qcut_reduce_workspace_bytes(int64_t n_coeffs, int n_obs) { return reduce_
 int qcut_reduce_launch(const int64_t* d_tallies, const qcut_pub_desc* d_pubs, const qcut_label_desc* d_labels,
                        int n_labels, const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                        const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                       void* d_workspace, int single_slot, void* stream) {
+                       void* d_workspace, int flags, void* stream) {
   if (!d_out || !d_workspace || n_labels < 0 || n_coeffs < 0)
     return set_error("qcut_reduce_launch: bad argument"), QCUT_ERR_INVALID;
   return launch_reduce<int64_t>(d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs,
-                                n_coeffs, n_obs, d_out, d_workspace, single_slot != 0, static_cast<cudaStream_t>(stream));
+                                n_coeffs, n_obs, d_out, d_workspace, (flags & QCUT_REDUCE_SINGLE_SLOT) != 0,
+                                (flags & QCUT_REDUCE_SEQUENTIAL) != 0, static_cast<cudaStream_t>(stream));
 }
 
 int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_pubs,
                                const qcut_label_desc* d_labels, int n_labels, const uint32_t* d_lookup_start,
                                const qcut_slot* d_lookup, const double* d_coeffs, int64_t n_coeffs, int n_obs,
-                               double* d_out, void* d_workspace, int single_slot, void* stream) {
+                               double* d_out, void* d_workspace, int flags, void* stream) {
   if (!d_out || !d_workspace || n_labels < 0 || n_coeffs < 0)
     return set_error("qcut_reduce_expvals_launch: bad argument"), QCUT_ERR_INVALID;
   return launch_reduce<double>(d_expvals, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs,
-                               n_coeffs, n_obs, d_out, d_workspace, single_slot != 0, static_cast<cudaStream_t>(stream));
+                               n_coeffs, n_obs, d_out, d_workspace, (flags & QCUT_REDUCE_SINGLE_SLOT) != 0,
+                               (flags & QCUT_REDUCE_SEQUENTIAL) != 0, static_cast<cudaStream_t>(stream));
+}
+
+int qcut_expvals_literal_launch(const qcut_plan* plan, const qcut_schedule* schedule, const uint8_t* d_data,
+                                double* d_expvals, int64_t n_expvals, void* stream) {
+  if (!plan || !schedule) return set_error("qcut_expvals_literal_launch: plan or schedule is NULL"), QCUT_ERR_INVALID;
+  if (n_expvals < 0 || (n_expvals > 0 && !d_expvals)) return set_error("qcut_expvals_literal_launch: bad output"), QCUT_ERR_INVALID;
+  if (schedule->n_tiles > 0 && !d_data) return set_error("qcut_expvals_literal_launch: d_data is NULL"), QCUT_ERR_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  schedule->last_stream = s;
+  schedule->launched = true;
+  // PUBs without shots write nothing: their expectation values stay 0 like the reference's (its loop does not run)
+  if (n_expvals > 0) QCUT_CUDA(cudaMemsetAsync(d_expvals, 0, sizeof(double) * (size_t)n_expvals, s));
+  return launch_literal(plan, d_data, schedule->d_pubs, schedule->n_pubs, d_expvals, s);
 }
 
 int qcut_quasi_launch(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_group_desc* d_groups,

@@ -149,7 +149,9 @@ constexpr int kMaxFastLabels = 4;  // subsystems handled by the straight-line pa
 
 // CHUNK coefficient tuples per CTA (one-chunk problems: reference order end to end).
 // L = number of subsystems when every observable has exactly one slot per subsystem (1..4), 0 = general.
-template <typename TallyT, int CHUNK, int L>
+// SEQ: one CTA walks ALL tuples, chunk after chunk, and its summing threads carry their running sums across the
+// chunks -- the reference's order for any number of tuples (rounding="reference"); gridDim.y must be 1.
+template <typename TallyT, int CHUNK, int L, bool SEQ>
 __global__ void __launch_bounds__(kReduceThreads)
 reduce_partial_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* __restrict__ pubs,
                       const qcut_label_desc* __restrict__ labels, int n_labels,
@@ -163,41 +165,40 @@ reduce_partial_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* _
   const int k_local = threadIdx.x % kReduceObs;
   const int i_local = threadIdx.x / kReduceObs;
   const int k = blockIdx.x * kReduceObs + k_local;
-  const int64_t i0 = (int64_t)blockIdx.y * CHUNK;
-  const int n_i = (int)min((int64_t)CHUNK, n_coeffs - i0);
-
-  if (k < n_obs) {
-    if constexpr (L > 0) {
-      SlotRef slots[L];
-      load_slots<L>(labels, lookup_start, lookup, k, slots);
-      for (int base = i_local; base < n_i; base += B * kStride) {
-        int64_t idx[B];
-        double term[B];
+  double sum = 0.0;  // running sum of the summing threads (threadIdx.x < kReduceObs)
+  const int64_t i_begin = SEQ ? 0 : (int64_t)blockIdx.y * CHUNK;
+  const int64_t i_end = SEQ ? n_coeffs : min(n_coeffs, i_begin + CHUNK);
+  for (int64_t i0 = i_begin; i0 < i_end || i0 == i_begin; i0 += CHUNK) {
+    const int n_i = (int)max((int64_t)0, min((int64_t)CHUNK, n_coeffs - i0));
+    if (k < n_obs) {
+      if constexpr (L > 0) {
+        SlotRef slots[L];
+        load_slots<L>(labels, lookup_start, lookup, k, slots);
+        for (int base = i_local; base < n_i; base += B * kStride) {
+          int64_t idx[B];
+          double term[B];
 #pragma unroll
-        for (int j = 0; j < B; ++j) idx[j] = i0 + min(base + j * kStride, n_i - 1);  // clamped: always valid
-        batch_terms<TallyT, L, B>(tallies, pubs, slots, coeffs, idx, term);
+          for (int j = 0; j < B; ++j) idx[j] = i0 + min(base + j * kStride, n_i - 1);  // clamped: always valid
+          batch_terms<TallyT, L, B>(tallies, pubs, slots, coeffs, idx, term);
 #pragma unroll
-        for (int j = 0; j < B; ++j)
-          if (base + j * kStride < n_i) s_term[k_local * ROW + base + j * kStride] = term[j];
+          for (int j = 0; j < B; ++j)
+            if (base + j * kStride < n_i) s_term[k_local * ROW + base + j * kStride] = term[j];
+        }
+      } else {
+        for (int ii = i_local; ii < n_i; ii += kStride)
+          s_term[k_local * ROW + ii] = general_term<TallyT>(tallies, pubs, labels, n_labels, lookup_start, lookup, coeffs, i0 + ii, k);
       }
-    } else {
-      for (int ii = i_local; ii < n_i; ii += kStride)
-        s_term[k_local * ROW + ii] = general_term<TallyT>(tallies, pubs, labels, n_labels, lookup_start, lookup, coeffs, i0 + ii, k);
     }
-  }
-  // zero the row tails up to a multiple of 8 so that phase 2 can run 8-wide without bound checks
-  // (adding +0.0 never changes a sum that started at +0.0)
-  const int n_pad = (n_i + 7) & ~7;
-  if (threadIdx.x < kReduceObs * 8) {
-    const int ii = n_i + threadIdx.x / kReduceObs;
-    if (ii < n_pad) s_term[(threadIdx.x % kReduceObs) * ROW + ii] = 0.0;
-  }
-  __syncthreads();
-  if (threadIdx.x < kReduceObs) {
-    const int kk = blockIdx.x * kReduceObs + threadIdx.x;
-    if (kk < n_obs) {
+    // zero the row tails up to a multiple of 8 so that phase 2 can run 8-wide without bound checks
+    // (adding +0.0 never changes a sum that started at +0.0)
+    const int n_pad = (n_i + 7) & ~7;
+    if (threadIdx.x < kReduceObs * 8) {
+      const int ii = n_i + threadIdx.x / kReduceObs;
+      if (ii < n_pad) s_term[(threadIdx.x % kReduceObs) * ROW + ii] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < kReduceObs && blockIdx.x * kReduceObs + threadIdx.x < n_obs) {
       const double* __restrict__ row = s_term + threadIdx.x * ROW;
-      double sum = 0.0;
       for (int ii = 0; ii < n_pad; ii += 8) {
         double v[8];
 #pragma unroll
@@ -205,8 +206,12 @@ reduce_partial_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) sum = __dadd_rn(sum, v[j]);  // strictly ascending i
       }
-      partial[(int64_t)blockIdx.y * n_obs + kk] = sum;
     }
+    if (SEQ) __syncthreads();  // the rows are overwritten by the next chunk
+  }
+  if (threadIdx.x < kReduceObs) {
+    const int kk = blockIdx.x * kReduceObs + threadIdx.x;
+    if (kk < n_obs) partial[(int64_t)blockIdx.y * n_obs + kk] = sum;
   }
 }
 
@@ -318,21 +323,30 @@ template <typename TallyT, int L>
 static int launch_level(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qcut_label_desc* d_labels,
                         int n_labels, const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                         const double* d_coeffs, int64_t n_coeffs, int n_obs, double* partial, int64_t chunks,
-                        cudaStream_t stream) {
-  if (chunk_size(n_coeffs) == kReduceChunk) {
-    static bool configured_dev[64] = {};
+                        bool sequential, cudaStream_t stream) {
+  if (sequential || chunk_size(n_coeffs) == kReduceChunk) {
+    static bool configured_dev[64][2] = {};
     int dev__ = 0;
     QCUT_CUDA(cudaGetDevice(&dev__));
-    bool& configured = configured_dev[dev__ & 63];  // the attribute is per device
+    const bool seq = sequential && n_coeffs > kReduceChunk;
+    bool& configured = configured_dev[dev__ & 63][seq ? 1 : 0];  // the attribute is per device
     const size_t smem = sizeof(double) * kReduceObs * (kReduceChunk + 10);
     if (!configured) {
-      QCUT_CUDA(cudaFuncSetAttribute(reduce_partial_kernel<TallyT, kReduceChunk, L>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (seq)
+        QCUT_CUDA(cudaFuncSetAttribute(reduce_partial_kernel<TallyT, kReduceChunk, L, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else
+        QCUT_CUDA(cudaFuncSetAttribute(reduce_partial_kernel<TallyT, kReduceChunk, L, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;
     }
     const dim3 grid((n_obs + kReduceObs - 1) / kReduceObs, (unsigned)chunks);
-    reduce_partial_kernel<TallyT, kReduceChunk, L><<<grid, kReduceThreads, smem, stream>>>(
-        d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, partial);
+    if (seq)
+      reduce_partial_kernel<TallyT, kReduceChunk, L, true><<<grid, kReduceThreads, smem, stream>>>(
+          d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, partial);
+    else
+      reduce_partial_kernel<TallyT, kReduceChunk, L, false><<<grid, kReduceThreads, smem, stream>>>(
+          d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, n_obs, partial);
   } else {
     const dim3 grid((n_obs + 31) / 32, (unsigned)chunks);
     reduce_stream_kernel<TallyT, L><<<grid, kStreamWarps * 32, 0, stream>>>(
@@ -348,9 +362,10 @@ template <typename TallyT>
 int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qcut_label_desc* d_labels,
                   int n_labels, const uint32_t* d_lookup_start, const qcut_slot* d_lookup,
                   const double* d_coeffs, int64_t n_coeffs, int n_obs, double* d_out,
-                  void* d_workspace, bool single_slot, cudaStream_t stream) {
+                  void* d_workspace, bool single_slot, bool sequential, cudaStream_t stream) {
   if (n_obs <= 0) return QCUT_OK;
-  const int64_t chunks = num_chunks(n_coeffs);
+  // sequential: one CTA column walks all tuples end to end -> the reference's summation order for any n_coeffs
+  const int64_t chunks = sequential ? 1 : num_chunks(n_coeffs);
   if (chunks > 65535) {
     set_error("qcut_reduce_launch: too many coefficients per rank");
     return QCUT_ERR_INVALID;
@@ -360,7 +375,7 @@ int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qc
   int rc;
 #define QCUT_LEVEL(LV)                                                                                              \
   rc = launch_level<TallyT, LV>(d_tallies, d_pubs, d_labels, n_labels, d_lookup_start, d_lookup, d_coeffs, n_coeffs, \
-                                n_obs, partial, chunks, stream)
+                                n_obs, partial, chunks, sequential, stream)
   switch (level) {
     case 1: QCUT_LEVEL(1); break;
     case 2: QCUT_LEVEL(2); break;
@@ -385,10 +400,10 @@ int launch_reduce(const TallyT* d_tallies, const qcut_pub_desc* d_pubs, const qc
 
 template int launch_reduce<int64_t>(const int64_t*, const qcut_pub_desc*, const qcut_label_desc*, int,
                                     const uint32_t*, const qcut_slot*, const double*, int64_t, int,
-                                    double*, void*, bool, cudaStream_t);
+                                    double*, void*, bool, bool, cudaStream_t);
 template int launch_reduce<double>(const double*, const qcut_pub_desc*, const qcut_label_desc*, int,
                                    const uint32_t*, const qcut_slot*, const double*, int64_t, int,
-                                   double*, void*, bool, cudaStream_t);
+                                   double*, void*, bool, bool, cudaStream_t);
 
 size_t reduce_workspace_bytes(int64_t n_coeffs, int n_obs) {
   const size_t chunks = (size_t)num_chunks(n_coeffs);

@@ -16,6 +16,7 @@ Objects are recognised by protocol, so real Qiskit objects and the stand-ins of
 
 from __future__ import annotations
 
+import os
 from collections.abc import Mapping, Sequence
 
 import numpy as np
@@ -104,6 +105,7 @@ def reconstruct_expectation_values(
     observables,
     *,
     process_group=None,
+    rounding: str | None = None,
 ) -> list[float]:
     r"""Reconstruct expectation values from the results of the cutting subexperiments.
 
@@ -121,6 +123,13 @@ def reconstruct_expectation_values(
             coefficients than balanced slices need, the ranks split the PUBs by bytes instead and
             all-reduce the exact int64 tally table (``distributed`` module docstring).  Without it
             the call is single-process, exactly like the reference.
+        rounding: ``"exact"`` (default; environment variable ``QCUT_ROUNDING`` overrides the default) -- every
+            per-subexperiment expectation value is ``tally / shots`` from exact integer tallies, which is closer to
+            the true sample mean than the reference's value; ``"reference"`` -- reproduce the reference's own
+            fp64 arithmetic, the shot-by-shot ``+= (1 / shots) * sign`` accumulation (``:159``) and the strictly
+            sequential sum over coefficients (``:168``), so that a single-process call returns the reference's
+            result **bit for bit** (about 10x slower kernels; with a process group the per-rank partial sums are
+            still added by the all-reduce).
 
     Returns:
         ``list`` of ``numpy.float64``, one expectation value per input observable.
@@ -158,6 +167,11 @@ def reconstruct_expectation_values(
 
     from . import _lib, distributed, engine, quasi
 
+    if rounding is None:
+        rounding = os.environ.get("QCUT_ROUNDING", "exact") or "exact"
+    if rounding not in ("exact", "reference"):
+        raise ValueError("rounding must be 'exact' or 'reference'")
+    literal = rounding == "reference"
     rank, world = distributed.rank_and_world(process_group)
     result_list = [results_dict[label] for label in labels]
     collection_list = [collections[label] for label in labels]
@@ -165,9 +179,9 @@ def reconstruct_expectation_values(
         if len(coeffs) == 0 or not labels:
             return list(np.zeros(n_obs))  # the reference's loops do not execute: expvals stay 0 (:133-170)
         if all(v1):
-            out = quasi.reconstruct_v1(result_list, collection_list, coeffs, 0, len(coeffs), n_obs)
+            out = quasi.reconstruct_v1(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, sequential=literal)
         else:
-            out = engine.stage_v2(result_list, collection_list, coeffs, 0, len(coeffs), n_obs).run()
+            out = engine.stage_v2(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, rounding=rounding).run()
         return list(out.cpu().numpy())
 
     # ---- sharded over the ranks of the process group: every rank makes the same call -----------------
@@ -179,7 +193,7 @@ def reconstruct_expectation_values(
     mode = "coefficients"
     try:
         sharding = engine.plan_sharding(result_list, collection_list, len(coeffs), rank, world,
-                                        allow_tally_mode=not any(v1))
+                                        allow_tally_mode=not any(v1) and not literal)
         mode = sharding.mode
     except Exception as exc:  # noqa: BLE001 - re-raised below, after the collective
         error = exc
@@ -202,10 +216,11 @@ def reconstruct_expectation_values(
             try:
                 if sharding.i_hi > sharding.i_lo and labels:
                     if all(v1):
-                        part = quasi.reconstruct_v1(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs)
+                        part = quasi.reconstruct_v1(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs,
+                                                    sequential=literal)
                     else:
                         part = engine.stage_v2(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs,
-                                               collected=sharding.collected or None).run()
+                                               collected=sharding.collected or None, rounding=rounding).run()
                     out = torch.zeros(n_obs + 1, dtype=torch.float64, device="cuda")
                     out[:n_obs] = part
             except Exception as exc:  # noqa: BLE001

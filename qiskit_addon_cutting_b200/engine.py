@@ -270,10 +270,19 @@ class Schedule:
 class DeviceBatch:
     """One rank's share of a reconstruction, resident in HBM."""
 
-    def __init__(self, tables: HostTables, data, *, flags: int = 0, k1_pubs: np.ndarray | None = None):
+    def __init__(self, tables: HostTables, data, *, flags: int = 0, k1_pubs: np.ndarray | None = None,
+                 rounding: str = "exact"):
         """``k1_pubs`` (tally-table sharding): the PUB pieces THIS rank tallies -- descriptors with this rank's
         data offsets and shot counts but the global ``tally_offset`` -- while ``tables.pubs`` stays the complete
-        table the product/sum kernel reads after the tally table has been all-reduced."""
+        table the product/sum kernel reads after the tally table has been all-reduced.
+
+        ``rounding``: ``"exact"`` -- int64 tallies, ``E = tally / shots`` by one correctly rounded division, tuples
+        summed in the reference's order up to 1024 of them (a fixed chunking above); ``"reference"`` -- every
+        (PUB, term) chain accumulated shot by shot in fp64 and the tuples summed strictly in order, i.e. the
+        reference's own arithmetic (``cutting_reconstruction.py:159,168``), bit for bit."""
+        if rounding not in ("exact", "reference"):
+            raise ValueError("rounding must be 'exact' or 'reference'")
+        self.rounding = rounding
         self.tables = tables
         if k1_pubs is None:
             k1_pubs = tables.k1_pubs
@@ -292,6 +301,7 @@ class DeviceBatch:
         ws = _lib.load().qcut_reduce_workspace_bytes(len(tables.coeffs), tables.n_obs)
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device="cuda")
         self.tally_launches = 0
+        self.expvals = None  # fp64 per-(PUB, term) expectation values of the reference-rounding mode
 
     def launch_tally(self) -> int:
         """K1 on the current stream: exact int64 sign tallies of every (PUB, term).  Returns #kernels launched."""
@@ -311,12 +321,28 @@ class DeviceBatch:
         self.tally_launches = n.value
         return n.value
 
+    def launch_literal(self) -> int:
+        """K1 with the reference's rounding on the current stream: fp64 ``expvals[pub.tally_offset + t]``."""
+        if self.expvals is None:
+            self.expvals = torch.empty(self.tables.n_tallies + 1, dtype=torch.float64, device="cuda")
+        check(
+            _lib.load().qcut_expvals_literal_launch(
+                self.plan.handle, self.schedule.handle, self.data.data_ptr(), self.expvals.data_ptr(),
+                self.tables.n_tallies, _stream_ptr(),
+            ),
+            "qcut_expvals_literal_launch",
+        )
+        return 1
+
     def launch_reduce(self) -> int:
         """K2 on the current stream: this rank's partial ``out[k]``.  Returns #kernels launched (2)."""
         t = self.tables
+        literal = self.rounding == "reference"
+        flags = (_lib.REDUCE_SINGLE_SLOT if t.single_slot else 0) | (_lib.REDUCE_SEQUENTIAL if literal else 0)
+        fn = _lib.load().qcut_reduce_expvals_launch if literal else _lib.load().qcut_reduce_launch
         check(
-            _lib.load().qcut_reduce_launch(
-                self.tallies.data_ptr(),
+            fn(
+                self.expvals.data_ptr() if literal else self.tallies.data_ptr(),
                 self.schedule.d_pubs if self.k2_pubs is None else self.k2_pubs.data_ptr(),
                 self.labels.data_ptr(),
                 len(t.labels),
@@ -327,18 +353,21 @@ class DeviceBatch:
                 t.n_obs,
                 self.out.data_ptr(),
                 self.workspace.data_ptr(),
-                int(t.single_slot),
+                flags,
                 _stream_ptr(),
             ),
             "qcut_reduce_launch",
         )
         if t.n_obs <= 0:
             return 0
-        n_chunks = 1 if len(t.coeffs) <= 1024 else -(-len(t.coeffs) // 256)
+        n_chunks = 1 if (literal or len(t.coeffs) <= 1024) else -(-len(t.coeffs) // 256)
         return 3 if n_chunks > 32 else 2
 
     def run(self) -> torch.Tensor:
-        self.launch_tally()
+        if self.rounding == "reference":
+            self.launch_literal()
+        else:
+            self.launch_tally()
         self.launch_reduce()
         return self.out[: self.tables.n_obs]
 
@@ -732,7 +761,7 @@ def _stage_simple(tables: HostTables, arrays: HostArrays) -> torch.Tensor:
 
 
 def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
-             *, flags: int = 0, collected: dict | None = None) -> DeviceBatch:
+             *, flags: int = 0, collected: dict | None = None, rounding: str = "exact") -> DeviceBatch:
     """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM.
 
     Large inputs: the PUBs are walked block by block (``csrc/pyhelper.c``); background threads hand every walked
@@ -751,10 +780,10 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
             with _staging_lock(torch.cuda.current_device()):
                 data = _stage_simple(tables, arrays)
             t_staged = time.perf_counter()
-            batch = DeviceBatch(tables, data, flags=flags)
+            batch = DeviceBatch(tables, data, flags=flags, rounding=rounding)
             batch.keepalive = arrays.keep
             last_stage_trace = {"walk_s": t_walked - t_start, "stage_s": t_staged - t_walked,
-                                "tables_s": time.perf_counter() - t_staged, "path": "simple"}
+                                "tables_s": time.perf_counter() - t_staged, "path": "simple", "dedup": tables.dedup}
             return batch
     # The pinned ring is shared by the calls of a process on one device: concurrent callers (Python threads)
     # take turns for the staging phase -- it is PCIe bound anyway -- and run their kernels independently.
@@ -769,7 +798,7 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
         # plan lookup / schedule upload proceed while the last blocks are still in flight
         t_walked = time.perf_counter()
         try:
-            batch = DeviceBatch(tables, stager, flags=flags)
+            batch = DeviceBatch(tables, stager, flags=flags, rounding=rounding)
         finally:
             t_batch = time.perf_counter()
             stager.finish(raise_errors=False)
@@ -778,6 +807,7 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
     last_stage_trace = {
         "walk_s": t_walked - t_start, "tables_s": t_batch - t_walked, "wait_s": time.perf_counter() - t_batch,
         "blocks": [(b, s - t_start, e - t_start) for b, s, e in stager.block_seconds], "path": "pipelined",
+        "dedup": tables.dedup,
     }
     return batch
 

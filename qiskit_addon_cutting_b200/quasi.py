@@ -30,7 +30,8 @@ def _limbs(value: int, n: int) -> list[int]:
     return [(value >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(n)]
 
 
-def reconstruct_v1(results: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int) -> torch.Tensor:
+def reconstruct_v1(results: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
+                   *, sequential: bool = False) -> torch.Tensor:
     _lib.require_device()
     lib = _lib.load()
     # First pass: split outcomes, find limb counts.
@@ -106,7 +107,8 @@ def reconstruct_v1(results: list, collections: list, coeffs: np.ndarray, i_lo: i
         lib.qcut_reduce_expvals_launch(
             expvals.data_ptr(), d_pubs.data_ptr(), d_labels.data_ptr(), len(label_rows), d_ls.data_ptr(),
             d_lk.data_ptr(), d_coeffs.data_ptr(), i_hi - i_lo, n_obs, out.data_ptr(), ws.data_ptr(),
-            int(np.all(np.diff(np.array(lookup_start, dtype=np.int64)) == 1)), stream,
+            (_lib.REDUCE_SINGLE_SLOT if np.all(np.diff(np.array(lookup_start, dtype=np.int64)) == 1) else 0)
+            | (_lib.REDUCE_SEQUENTIAL if sequential else 0), stream,
         ),
         "qcut_reduce_expvals_launch",
     )

@@ -29,7 +29,7 @@ def test_header_symbols_exported(lib):
 def test_abi_version_and_structs(lib):
     from qiskit_addon_cutting_b200 import _lib
 
-    assert lib.qcut_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.qcut_abi_version() == _lib.ABI_VERSION == 4
     header = (ROOT / "include" / "qcut_b200.h").read_text()
     assert f"#define QCUT_TILE_SHOTS {_lib.TILE_SHOTS}" in header
     assert f"#define QCUT_MAX_OBS_BYTES {_lib.MAX_OBS_BYTES}" in header

@@ -130,3 +130,12 @@ def test_expectation_values_at_a_million_shots_vs_literal_oracle(lib, shots, exa
         assert [v.hex() for v in ours] == [v.hex() for v in literal_vals]
     else:
         assert np.max(np.abs(ours - literal_vals)) <= 2e-11 * kappa
+    # rounding="reference": the chain kernel reproduces the reference's arithmetic bit for bit at 10^6 shots, both per
+    # (PUB, term) and after the product / sum
+    lit = engine.DeviceBatch(tables, data, rounding="reference")
+    lit_out = lit.run().cpu().numpy()
+    assert [v.hex() for v in lit.expvals[: tables.n_tallies].cpu().numpy()] == [v.hex() for v in e_seq]
+    assert [v.hex() for v in lit_out] == [v.hex() for v in literal_vals]
+    print(f"\nS={shots}: max|ours-literal|={np.max(np.abs(ours - literal_vals)):.3e} max|ours-exact|="
+          f"{np.max(np.abs(ours - exact_vals)):.3e} max|literal-exact|={np.max(np.abs(literal_vals - exact_vals)):.3e} "
+          f"max|E|={np.max(np.abs(exact_vals)):.3e} reference-rounding mode: bit-identical")

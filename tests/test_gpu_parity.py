@@ -265,3 +265,45 @@ def test_duplicate_pubs_are_staged_and_tallied_once(lib, monkeypatch, pipelined)
     assert _hex(got) == _hex(oracle.reconstruct_exact(dup, coefficients, observables))
     monkeypatch.setattr(engine, "_DEDUP", False)
     assert _hex(got) == _hex(reconstruct_expectation_values(dup, coefficients, observables))
+
+
+# ---- rounding="reference": the reference's own fp64 arithmetic, bit for bit -------------------------------------
+@pytest.mark.parametrize("name", _golden.CASE_NAMES)
+def test_reference_rounding_is_bit_identical_to_the_reference(lib, name):
+    """Fixtures hold what the reference's own source text returned (tests/golden/make_golden.py); shot counts are not
+    powers of two, so the reference's shot-by-shot accumulation differs from tally/S in the last bits -- the
+    reference-rounding mode reproduces exactly those bits (cutting_reconstruction.py:159,168)."""
+    case = _golden.load_case(name)
+    out = reconstruct_expectation_values(case["results"], case["coefficients"], case["observables"], rounding="reference")
+    assert _hex(out) == _hex(case["reference_expvals"])
+
+
+def test_reference_rounding_for_every_row_width_and_many_tuples(lib, monkeypatch):
+    """Widths 1..33 bytes (all word-count variants of the chain kernel), multi-slot means, zero-shot PUBs, C > 1024
+    (sequential K2), and the environment-variable default: bit-identical to the oracle's literal restatement, which
+    tests/test_oracle.py pins to the reference's text."""
+    rng = np.random.default_rng(4242)
+    for nbits, qbits, shots in ((3, 1, 100), (20, 11, 77), (33, 2, 130), (64, 8, 257), (100, 1, 90), (264, 3, 50)):
+        observables = {"A": _cases.random_paulis(rng, 9, nbits, 1, min(nbits, 30), "Z"),
+                       "B": _cases.random_paulis(rng, 9, 5, 0, 5)}
+        coefficients = _cases.random_coefficients(rng, 5)
+        results = _cases.make_results(observables, 5, lambda label, i, g: shots + i if i != 2 else 0, qbits,
+                                      seed=int(rng.integers(1 << 30)))
+        out = reconstruct_expectation_values(results, coefficients, observables, rounding="reference")
+        assert _hex(out) == _hex(oracle.reconstruct_literal(results, coefficients, observables)), nbits
+    # duplicates in the observable list -> multi-slot lookups (np.mean over slots), identity-only groups
+    results, coefficients, observables = _cases.SMALL_CASES["odd_widths"]()
+    assert _hex(reconstruct_expectation_values(results, coefficients, observables, rounding="reference")) == \
+        _hex(oracle.reconstruct_literal(results, coefficients, observables))
+    # more than 1024 tuples: the default mode sums chunks, the reference mode stays strictly sequential
+    observables = {"A": _cases.random_paulis(rng, 5, 8, 1, 4, "Z"), "B": _cases.random_paulis(rng, 5, 6, 1, 4, "Z")}
+    C = 2300
+    coefficients = _cases.random_coefficients(rng, C, kappa=81.0)
+    results = _cases.make_results(observables, C, 21, 2, seed=79)
+    want = oracle.reconstruct_literal(results, coefficients, observables)
+    monkeypatch.setenv("QCUT_ROUNDING", "reference")
+    assert _hex(reconstruct_expectation_values(results, coefficients, observables)) == _hex(want)
+    monkeypatch.delenv("QCUT_ROUNDING")
+    assert np.max(np.abs(np.array(reconstruct_expectation_values(results, coefficients, observables)) - want)) <= 1e-12
+    with pytest.raises(ValueError):
+        reconstruct_expectation_values(results, coefficients, observables, rounding="fast")

@@ -376,6 +376,24 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
                 "k1_share_of_step": k1_ms / ms_per_step, "k2_plus_allreduce_ms": k2_ms,
                 "k1_kernels_per_launch": int(batch.tally_launches)}
 
+    # ---- opt-in reference-rounding mode on the full resident data (shot-ordered fp64 chains + sequential K2) ----
+    literal = None
+    if rank == 0 and world == 1:
+        lit = engine.DeviceBatch(tables, data, flags=args.plan_flags, rounding="reference")
+        lit.run()
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        lit_out = lit.run()
+        l1.record()
+        torch.cuda.synchronize()
+        lit_ms = l0.elapsed_time(l1)
+        literal = {"ms_per_step": lit_ms, "value": work_step / (lit_ms * 1e-3), "unit": UNIT,
+                   "max_abs_dev_vs_default_mode": float(np.max(np.abs(lit_out.cpu().numpy() - resident_out))),
+                   "what": "rounding='reference' on the same resident data: every (PUB, term) chain accumulated shot by shot in "
+                           "fp64 like cutting_reconstruction.py:159, tuples summed strictly in order (:168)"}
+        del lit, lit_out
+
     # ---- same-run parity, part 1: int64 tallies of a PUB sample against the C oracle (rank 0) ----------
     parity = None
     if rank == 0:
@@ -394,6 +412,7 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
         ref_vals = np.array(fn(sub_results, sub_pairs, w.observables))
         secs = time.perf_counter() - t
         ours_vals = np.array(reconstruct_expectation_values(sub_results, sub_pairs, w.observables))
+        lit_vals = np.array(reconstruct_expectation_values(sub_results, sub_pairs, w.observables, rounding="reference"))
         exact_vals = np.array(oracle.reconstruct_exact(sub_results, sub_pairs, w.observables))
         kappa_sub = float(np.abs(tables.coeffs[:c]).sum())
         parity.update({
@@ -406,6 +425,7 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
             "reference_vs_exact": float(np.max(np.abs(ref_vals - exact_vals))),
             "bit_identical_to_exact_oracle": bool(np.array_equal(ours_vals, exact_vals)),
             "within_1e-12_of_reference": bool(np.max(np.abs(ours_vals - ref_vals)) <= 1e-12),
+            "reference_rounding_mode_bit_identical_to_reference": bool(np.array_equal(lit_vals, ref_vals)),
         })
         cpu = {"value": sample_work(w, c, s) / secs, "unit": UNIT, "cores": 1, "kind": kind, "seconds": secs,
                "sample": f"{c} tuples x {s} shots of the same resident data through "
@@ -460,7 +480,7 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
         "config": dict(w_global.describe(), l2="flushed_between_steps" if fits_l2 else "inputs_exceed_l2",
                        bytes_per_gpu=int(tables.data_bytes), work_per_gpu=int(tables.work),
                        coefficient_tuples_total=int(len(coeffs_global)), coefficient_tuples_this_rank=int(len(tables.coeffs))),
-        "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "parity": parity, "reference_rounding_mode": literal, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches) * steps, "gpu_launches_per_step": int(launches), "clocks": clocks,
         "checksum": float(np.sum(resident_out)),
     }
@@ -549,7 +569,7 @@ def ours_arm(args):
                 rec = measure(args, name, steps=args.per_config_steps, warmup=3, e2e_steps=max(3, args.e2e_steps),
                               cpu_seconds=min(args.cpu_seconds, 6.0), want_cpu=want_cpu, want_e2e=not args.no_e2e,
                               sample_clocks=False)
-                keep = ("value", "unit", "ms_per_step", "steps", "config", "roofline", "parity", "cpu_baseline", "e2e",
+                keep = ("value", "unit", "ms_per_step", "steps", "config", "roofline", "parity", "reference_rounding_mode", "cpu_baseline", "e2e",
                         "gpu_launches_per_step", "checksum")
                 rec = {k: rec[k] for k in keep}
             except Exception as exc:  # a failing shape must not take the headline line down with it

@@ -700,7 +700,10 @@ int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint
       return set_error("qcut_stage_h2d: arrays must be sorted by destination offset and must not overlap"), QCUT_ERR_INVALID;
   if (n_threads <= 0) n_threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
   size_t slot_bytes = (pinned_bytes / (size_t)n_threads) & ~(size_t)255;
-  while (n_threads > 1 && slot_bytes < ((size_t)1 << 20)) {
+  // slots of at least 512 KiB: smaller copies do not keep the PCIe link busy (QCUT_STAGING_MIN_SLOT_KB overrides)
+  const char* env_slot = std::getenv("QCUT_STAGING_MIN_SLOT_KB");
+  const size_t min_slot = (env_slot && *env_slot ? (size_t)std::max(4, std::atoi(env_slot)) : (size_t)512) << 10;
+  while (n_threads > 1 && slot_bytes < min_slot) {
     --n_threads;
     slot_bytes = (pinned_bytes / (size_t)n_threads) & ~(size_t)255;
   }

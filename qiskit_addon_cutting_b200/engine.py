@@ -642,23 +642,59 @@ def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_thread
 # Pinned staging ring of the end-to-end path, independent of the problem size.  Measured on cfg4 (14.3 GB per
 # call, PCIe ceiling of the box 55 GB/s).  One rank per host: 292 ms with 256 MiB written with streaming stores
 # (qcut_stage_h2d does that for rings >= 64 MiB per call), 308 ms with 128 MiB / 326 ms with 64 or 256 MiB and
-# ordinary stores, 352 ms with 32 MiB (pieces too small for PCIe).  Two ranks on one 24-core host: the host's
-# memory bandwidth is the limit, 415 ms with a 64 MiB ring that stays close to the last-level cache the DMA
-# engine reads from, 460-473 ms with streaming stores, 540 ms with 256 MiB and ordinary stores.
-# Hence: 256 MiB alone on a host, 64 MiB with local peers.
-def _default_staging_mb() -> int:
+# ordinary stores, 352 ms with 32 MiB (pieces too small for PCIe).  Several ranks on one host: the path is bound by
+# the host's memory bandwidth -- every shot byte is read from its BitArray, written to the ring and read again by
+# the DMA engine -- unless the ring stays in the caches: then only the first of the three passes touches DRAM.
+# Hence: 256 MiB alone on a host; with local peers each rank takes its share of HALF the last-level cache
+# (ordinary stores, so that the DMA engine finds the lines in the cache), cut into slots of >= 512 KiB.
+def _llc_bytes() -> int:
+    """Size of the last-level cache this process can count on (all L3 instances of the host), 32 MiB if unknown."""
+    total, seen = 0, set()
     try:
-        peers = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        base = "/sys/devices/system/cpu"
+        for cpu in os.listdir(base):
+            path = f"{base}/{cpu}/cache/index3"
+            if not cpu.startswith("cpu") or not cpu[3:].isdigit() or not os.path.isdir(path):
+                continue
+            with open(f"{path}/shared_cpu_list") as f:
+                key = f.read().strip()
+            if key in seen:
+                continue
+            seen.add(key)
+            with open(f"{path}/size") as f:
+                txt = f.read().strip().upper()
+            total += int(txt[:-1]) * {"K": 1 << 10, "M": 1 << 20, "G": 1 << 30}[txt[-1]] if txt[-1] in "KMG" else int(txt)
+    except (OSError, ValueError, KeyError):
+        total = 0
+    return total or (32 << 20)
+
+
+def _local_peers() -> int:
+    try:
+        return max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
     except ValueError:
-        peers = 1
-    return 256 if peers <= 1 else 64
+        return 1
 
 
-_STAGING_BYTES = int(os.environ.get("QCUT_STAGING_MB", "0") or 0) << 20 or _default_staging_mb() << 20
+def _default_staging_bytes() -> int:
+    peers = _local_peers()
+    if peers <= 1:
+        return 256 << 20
+    share = _llc_bytes() // (2 * peers)
+    return int(min(64 << 20, max(2 << 20, share))) & ~((1 << 20) - 1)
 
-# Gather threads per feeder (two feeders).  4 and 8 measured the same alone on a host; on an 8-GPU box with 32
-# cores 2 per feeder was no better than 8 (1.84 s vs 1.67 s per call and rank): that host is bandwidth bound.
-_STAGING_THREADS = int(os.environ.get("QCUT_STAGING_THREADS", "0") or 0) or 8
+
+def _default_staging_threads() -> int:
+    """Gather threads per feeder (two feeders).  Alone on a host 4 and 8 measured the same; with local peers the
+    ranks share the cores: two feeders x threads x peers should not exceed them."""
+    peers = _local_peers()
+    if peers <= 1:
+        return 8
+    return max(1, min(8, (os.cpu_count() or 8) // (2 * peers)))
+
+
+_STAGING_BYTES = int(os.environ.get("QCUT_STAGING_MB", "0") or 0) << 20 or _default_staging_bytes()
+_STAGING_THREADS = int(os.environ.get("QCUT_STAGING_THREADS", "0") or 0) or _default_staging_threads()
 _BLOCK_PUBS = 2048  # PUBs in the first staging block of a label (~1 ms of attribute walk); later blocks grow 4x
 
 

@@ -197,7 +197,15 @@ def reconstruct_expectation_values(
         mode = sharding.mode
     except Exception as exc:  # noqa: BLE001 - re-raised below, after the collective
         error = exc
-    if error is None and mode == "tallies":
+    # The two sharding modes end in different collectives, and a rank that failed while looking at its inputs has
+    # not decided at all: agree first (one tiny all-reduce), so that either every rank raises here or every rank
+    # enters the same collective below.
+    failed_anywhere = distributed.agree_on_failure(error is not None, process_group, world)
+    if error is not None:
+        raise error
+    if failed_anywhere:
+        raise distributed.RemoteRankError("reconstruct_expectation_values failed on at least one rank of the process group")
+    if mode == "tallies":
         # few coefficients: byte-balanced (label, PUB, shot range) pieces, all-reduce of the int64 tally table
         batch = None
         try:

@@ -175,6 +175,16 @@ def all_reduce_with_flag(payload: torch.Tensor, failed: bool, process_group, wor
     return payload
 
 
+def agree_on_failure(failed: bool, process_group, world: int) -> bool:
+    """True on every rank if any rank reports a failure (an all-reduce of one flag; synchronises with the host)."""
+    if world <= 1:
+        return failed
+    backend = dist.get_backend(process_group)
+    flag = torch.tensor([1 if failed else 0], dtype=torch.int32, device="cuda" if backend == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=process_group)
+    return bool(flag.item())
+
+
 def check_flag(flag_value) -> None:
     if float(flag_value) != 0:
         raise RemoteRankError("reconstruct_expectation_values failed on at least one rank of the process group")

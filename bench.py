@@ -244,6 +244,30 @@ def committed_traffic(name: str, scale: float):
     return best or (None, None)
 
 
+def host_copy_ceiling(gib: float = 1.0, array_kib: int = 64) -> dict:
+    """STREAM-style copy ceiling of this host through the library's own gather (scripts/host_bw.py): ``gib`` GiB held
+    in separate ``array_kib`` KiB allocations copied into one buffer with all cores.  Staging does exactly this copy
+    (BitArrays -> pinned ring), so the summed e2e rate of the ranks of one host cannot exceed it."""
+    from qiskit_addon_cutting_b200 import _lib
+
+    lib = _lib.load()
+    size = array_kib << 10
+    n = int(gib * (1 << 30)) // size
+    arrays = [np.full(size, i & 0xFF, dtype=np.uint8) for i in range(n)]
+    src = np.array([a.ctypes.data for a in arrays], dtype=np.uint64)
+    nbytes = np.full(n, size, dtype=np.uint64)
+    offs = np.arange(n, dtype=np.uint64) * np.uint64(size)
+    dst = np.zeros(n * size, dtype=np.uint8)
+    threads = min(os.cpu_count() or 1, 32)
+    best = 0.0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        assert lib.qcut_gather_host(src.ctypes.data, nbytes.ctypes.data, offs.ctypes.data, n, dst.ctypes.data, threads) == 0
+        best = max(best, n * size / (time.perf_counter() - t0) / 1e9)
+    return {"copy_gbs": best, "threads": threads, "cpus": os.cpu_count(),
+            "what": f"{gib:g} GiB in {array_kib} KiB allocations copied into one buffer (bytes copied per second; read + write)"}
+
+
 def tally_parity(tables, data, tallies, *, max_work: float = 3e9, max_pubs: int = 256) -> dict:
     """A spread sample of PUBs recomputed by the C oracle on the SAME resident bytes: int64 tallies must be bit-exact.
     Also reports how far the reference's sequential ``+= (1/S) * sign`` arithmetic (restated in C, full shot counts)
@@ -444,6 +468,7 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
         else:
             pairs = W.coefficient_pairs(tables.coeffs)
             group = None
+        ceiling = host_copy_ceiling() if rank == 0 else None
         got = reconstruct_expectation_values(results, pairs, w.observables, process_group=group)  # warm-up (pinned buffer, plan cache)
         torch.cuda.synchronize()
         if world > 1:
@@ -462,6 +487,8 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
                "host_buffers": f"{2 * len(tables.pubs)} separate NumPy allocations per rank (one per BitArray)",
                "api": "reconstruct_expectation_values(results, coefficients, observables"
                       + (", process_group=WORLD): sharded public API + NCCL all-reduce" if world > 1 else ")"),
+               "host_copy_ceiling": ceiling,
+               "host_copy_frac": (world * h2d / (e2e_secs / e2e_steps) / 1e9 / ceiling["copy_gbs"]) if ceiling else None,
                "staging_path": engine.last_stage_trace.get("path"),
                "dedup_ratio": engine.last_stage_trace.get("dedup", {}).get("dedup_ratio")}
         # same bytes, same path: the API result must equal the resident-data result

@@ -54,6 +54,7 @@ struct JitKernel {
   std::vector<int> variants;  // representative group of every variant (multi-group kernels), empty otherwise
   int nb_obs = 0;
   bool staged = true;  // bulk-copy staged stream (shared-memory prefetch) vs direct global loads
+  bool split = false;  // 8-byte rows processed one 32x32 block at a time (block 1 parked in shared memory)
   int smem_bytes = 0;
 };
 

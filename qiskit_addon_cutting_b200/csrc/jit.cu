@@ -29,6 +29,7 @@ static const char* const kPrelude =
     ;
 
 constexpr uint32_t kMaxJitTerms = 384;  // packed 8-bit counters: ceil(T/4) registers per lane
+constexpr size_t kMaxSplitCross = 12;   // 8-byte rows are processed one block at a time while at most this many terms straddle the blocks
 
 bool jit_supports(const qcut_group_desc& gd) {
   const uint32_t nb = gd.nb_obs;
@@ -52,40 +53,75 @@ static std::string plane_name(uint32_t nb, uint32_t byte, uint32_t bit) {
 // term is either built from scratch (qp ^ its planes) or from the previous term's word XOR the planes
 // in which the two masks differ, whichever needs fewer LOP3 -- dense or structured mask sets (long
 // shared Z strings) share most of their work this way, at the cost of one live register.
-static void emit_terms(std::ostringstream& os, const std::string& name, const qcut_group_desc& gd, const uint8_t* masks) {
-  const uint32_t T = gd.n_terms, nb = gd.nb_obs, nacc = (T + 3) / 4;
-  auto row = [&](uint32_t t) { return masks + gd.mask_offset + (size_t)t * nb; };
-  auto weight = [&](uint32_t t) {
+namespace {
+struct TermEmitter {
+  std::ostringstream& os;
+  const qcut_group_desc& gd;
+  const uint8_t* masks;
+  uint32_t T, nb, nacc;
+  const uint8_t* row(uint32_t t) const { return masks + gd.mask_offset + (size_t)t * nb; }
+  int weight(uint32_t t, uint32_t b0, uint32_t b1) const {
     int w = 0;
-    for (uint32_t b = 0; b < nb; ++b) w += __builtin_popcount(row(t)[b]);
+    for (uint32_t b = b0; b < b1; ++b) w += __builtin_popcount(row(t)[b]);
     return w;
-  };
-  auto dist = [&](uint32_t s, uint32_t t) {
-    int d = 0;
-    for (uint32_t b = 0; b < nb; ++b) d += __builtin_popcount((unsigned)(row(s)[b] ^ row(t)[b]));
-    return d;
-  };
-  // evaluation order
-  std::vector<uint32_t> order;
-  std::vector<bool> incremental(T, false);
-  std::vector<bool> done(T, false);
-  uint32_t prev = 0;
-  for (uint32_t step = 0; step < T; ++step) {
-    uint32_t best = T;
-    int best_cost = 1 << 30;
-    bool best_inc = false;
-    for (uint32_t t = 0; t < T; ++t) {
-      if (done[t]) continue;
-      const int direct = weight(t);                            // planes XORed onto qp
-      const int inc = step ? dist(prev, t) : (1 << 29);        // planes XORed onto the previous word
-      const int cost = std::min(direct, inc);
-      if (cost < best_cost) { best_cost = cost; best = t; best_inc = inc < direct; }
-    }
-    done[best] = true;
-    incremental[best] = best_inc;
-    order.push_back(best);
-    prev = best;
   }
+  int dist(uint32_t s, uint32_t t, uint32_t b0, uint32_t b1) const {
+    int d = 0;
+    for (uint32_t b = b0; b < b1; ++b) d += __builtin_popcount((unsigned)(row(s)[b] ^ row(t)[b]));
+    return d;
+  }
+  void count(uint32_t t, const char* word) {
+    // term t lives in field t / NACC of packed register t % NACC: consecutive terms touch different
+    // registers, so their popcount -> add chains are independent
+    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(" << word << ")";
+    if (t / nacc) os << " << " << 8 * (t / nacc);
+    os << ";\n";
+  }
+  // Emit the terms of `which` restricted to mask bytes [b0, b1), chained in nearest-neighbour Hamming order.
+  // start_of(t): the expression a from-scratch evaluation starts with ("qp" or a kept partial word).  Chaining
+  // from the previous term is only allowed when both start from "qp" (chain_ok).  finish(t, "x") emits what
+  // happens to the finished word (count it, or keep it for the second half of the step).
+  template <class Start, class Finish>
+  void chain(const std::vector<uint32_t>& which, uint32_t b0, uint32_t b1, bool chain_ok, Start start_of, Finish finish,
+             const std::function<std::string(uint32_t, uint32_t)>& plane) {
+    std::vector<bool> done(T, false);
+    uint32_t prev = 0;
+    bool have_prev = false;
+    for (size_t step = 0; step < which.size(); ++step) {
+      uint32_t best = T;
+      int best_cost = 1 << 30;
+      bool best_inc = false;
+      for (uint32_t t : which) {
+        if (done[t]) continue;
+        const int direct = weight(t, b0, b1);
+        const int inc = (have_prev && chain_ok) ? dist(prev, t, b0, b1) : (1 << 29);
+        const int cost = std::min(direct, inc);
+        if (cost < best_cost) { best_cost = cost; best = t; best_inc = inc < direct; }
+      }
+      done[best] = true;
+      const uint8_t* cur = row(best);
+      const uint8_t* old = have_prev ? row(prev) : cur;
+      os << "    x = " << (best_inc ? std::string("x") : start_of(best));
+      for (uint32_t byte = b0; byte < b1; ++byte)
+        for (uint32_t bit = 0; bit < 8; ++bit) {
+          const unsigned sel = best_inc ? (unsigned)(cur[byte] ^ old[byte]) : (unsigned)cur[byte];
+          if ((sel >> bit) & 1u) os << " ^ " << plane(byte, bit);
+        }
+      os << ";\n";
+      finish(best, "x");
+      prev = best;
+      have_prev = true;
+    }
+  }
+};
+}  // namespace
+
+// Returns true when the split form (run0 / run1) was emitted.
+static bool emit_terms(std::ostringstream& os, const std::string& name, const qcut_group_desc& gd, const uint8_t* masks) {
+  const uint32_t T = gd.n_terms, nb = gd.nb_obs, nacc = (T + 3) / 4;
+  TermEmitter em{os, gd, masks, T, nb, nacc};
+  std::vector<uint32_t> all(T);
+  for (uint32_t t = 0; t < T; ++t) all[t] = t;
   os << "// " << T << " terms on " << nb << "-byte rows\n";
   os << "struct " << name << " {\n";
   os << "  static const int T = " << T << ";\n  static const int NACC = " << nacc << ";\n";
@@ -93,24 +129,45 @@ static void emit_terms(std::ostringstream& os, const std::string& name, const qc
   os << "  static QCUT_MDEV void run(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, "
         "const uint32_t qp, uint32_t* __restrict__ acc) {\n";
   os << "    (void)Q;\n    uint32_t x;\n";
-  for (uint32_t i = 0; i < T; ++i) {
-    const uint32_t t = order[i];
-    const uint8_t* cur = row(t);
-    const uint8_t* old = i ? row(order[i - 1]) : cur;
-    os << "    x = " << (incremental[t] ? "x" : "qp");
-    for (uint32_t byte = 0; byte < nb; ++byte)
-      for (uint32_t bit = 0; bit < 8; ++bit) {
-        const unsigned sel = incremental[t] ? (unsigned)(cur[byte] ^ old[byte]) : (unsigned)cur[byte];
-        if ((sel >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
-      }
-    os << ";\n";
-    // term t lives in field t / NACC of packed register t % NACC: consecutive terms touch different
-    // registers, so their popcount -> add chains are independent
-    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(x)";
-    if (t / nacc) os << " << " << 8 * (t / nacc);
-    os << ";\n";
+  em.chain(all, 0, nb, true, [](uint32_t) { return std::string("qp"); },
+           [&](uint32_t t, const char* w) { em.count(t, w); },
+           [&](uint32_t byte, uint32_t bit) { return plane_name(nb, byte, bit); });
+  os << "  }\n";
+  // 8-byte rows, one block at a time (qcut_lane_tile_split): block-0 terms and the block-0 half of the cross
+  // terms in run0 (their partial words wait in K[]), block-1 terms and the rest of the cross terms in run1.
+  // Only worth it while few terms straddle the two halves of the row.
+  std::vector<uint32_t> lo, hi, cross;
+  if (nb == 8) {
+    for (uint32_t t = 0; t < T; ++t) {
+      const bool in_lo = em.weight(t, 0, 4) > 0, in_hi = em.weight(t, 4, 8) > 0;
+      (in_lo && in_hi ? cross : in_hi ? hi : lo).push_back(t);  // identity terms count with block 0
+    }
   }
-  os << "  }\n};\n\n";
+  const bool split = nb == 8 && cross.size() <= kMaxSplitCross;
+  os << "  static const int SPLIT = " << (split ? 1 : 0) << ";\n";
+  os << "  static const int NKEEP = " << (split ? cross.size() : 0) << ";\n";
+  if (split) {
+    std::vector<int> slot(T, -1);
+    for (size_t i = 0; i < cross.size(); ++i) slot[cross[i]] = (int)i;
+    auto p0 = [&](uint32_t byte, uint32_t bit) { return "P[" + std::to_string(8 * byte + bit) + "]"; };
+    auto p1 = [&](uint32_t byte, uint32_t bit) { return "P[" + std::to_string(8 * (byte - 4) + bit) + "]"; };
+    os << "  static QCUT_MDEV void run0(const uint32_t* __restrict__ P, const uint32_t qp, uint32_t* __restrict__ acc, "
+          "uint32_t* __restrict__ K) {\n    (void)K;\n    uint32_t x;\n";
+    em.chain(lo, 0, 4, true, [](uint32_t) { return std::string("qp"); },
+             [&](uint32_t t, const char* w) { em.count(t, w); }, p0);
+    em.chain(cross, 0, 4, true, [](uint32_t) { return std::string("qp"); },
+             [&](uint32_t t, const char* w) { os << "    K[" << slot[t] << "] = " << w << ";\n"; }, p0);
+    os << "  }\n";
+    os << "  static QCUT_MDEV void run1(const uint32_t* __restrict__ P, const uint32_t qp, uint32_t* __restrict__ acc, "
+          "const uint32_t* __restrict__ K) {\n    (void)K;\n    uint32_t x;\n";
+    em.chain(hi, 4, 8, true, [](uint32_t) { return std::string("qp"); },
+             [&](uint32_t t, const char* w) { em.count(t, w); }, p1);
+    em.chain(cross, 4, 8, false, [&](uint32_t t) { return "K[" + std::to_string(slot[t]) + "]"; },
+             [&](uint32_t t, const char* w) { em.count(t, w); }, p1);
+    os << "  }\n";
+  }
+  os << "};\n\n";
+  return split;
 }
 
 // One kernel for many small groups: every group becomes a __noinline__ device function (so that
@@ -156,17 +213,23 @@ std::string generate_multi_source(const std::vector<const qcut_group_desc*>& gds
 
 // The translation unit for one group.  Pure host code.
 std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out,
-                                   bool staged, int threads, int prefetch) {
+                                   bool staged, int threads, int prefetch, bool allow_split, bool* split_out) {
   if (!jit_supports(gd)) return std::string();
   const uint32_t T = gd.n_terms, nb = gd.nb_obs;
-  // Register budget: 32 per block + packed counters + ~28 of addressing / temporaries.
-  int min_blocks = ((nb > 4 ? 64 : 32) + (int)((T + 3) / 4) + 28 > 128) ? 1 : 2;
+  std::ostringstream terms;
+  const bool split = emit_terms(terms, "Terms", gd, masks) && allow_split && !staged && prefetch == 0;
+  if (split_out) *split_out = split;
+  // Register budget: 32 per live block + packed counters + ~28 of addressing / temporaries.
+  const int budget = ((nb > 4 && !split) ? 64 : 32) + (int)((T + 3) / 4) + 28;
+  int min_blocks = budget > 128 ? 1 : 2;
+  if (split && threads * 3 * (budget + 8) <= 65536) min_blocks = 3;  // one block at a time: three CTAs share an SM
   if (min_blocks_out && *min_blocks_out > 0) min_blocks = *min_blocks_out;  // explicit override
   if (min_blocks_out) *min_blocks_out = min_blocks;
 
   std::ostringstream os;
+  if (staged || prefetch > 0) os << "#define QCUT_WITH_VARIANTS 1\n";
   os << kPrelude << "\n";
-  emit_terms(os, "Terms", gd, masks);
+  os << terms.str();
   if (nb > 8) {
     // Wide rows: 4 warps per CTA (2 for rows of more than 16 bytes), per-warp raw + plane buffers in dynamic
     // shared memory.
@@ -209,7 +272,31 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   }
   os << "#ifndef QCUT_HOST_EMU\n";
   os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n";
-  if (staged) {
+  if (split) {
+    // One 32x32 block at a time; the raw words of block 1 wait in the lane's column of a per-warp parking area
+    // (32 x 32 words of dynamic shared memory per warp).
+    os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  extern __shared__ __align__(16) uint32_t qcut_smem[];\n"
+          "  const int lane = threadIdx.x & 31;\n"
+          "  uint32_t* __restrict__ park = qcut_smem + (threadIdx.x >> 5) * 1024 + lane;\n"
+          "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+          "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
+          "       tile += n_warps) {\n"
+          "    const QcutTile te = tiles[tile];\n"
+          "    const QcutPub pub = pubs[te.pub];\n"
+          "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+          "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+          "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
+          "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "    uint32_t acc[Terms::NACC];\n"
+          "    qcut_lane_tile_split<Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc, park);\n"
+          "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
+          "  }\n"
+          "}\n";
+  } else if (staged) {
     // Bulk-copy staged stream: one staging buffer + one mbarrier per warp in dynamic shared memory.
     os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
           "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
@@ -289,9 +376,13 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   os << "#else  // host emulation entry: one lane of one tile, unpacked odd counts\n";
   os << "extern \"C\" int qcut_emu_lane_tile(const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
         "                                  uint32_t* odd_out) {\n"
-        "  uint32_t acc[Terms::NACC];\n"
-        "  qcut_lane_tile<Terms::NB, Terms>(obs, qpd, nbq, ns, lane, acc);\n"
-        "  for (int t = 0; t < Terms::T; ++t) odd_out[t] = (acc[t % Terms::NACC] >> (8 * (t / Terms::NACC))) & 0xFFu;\n"
+        "  uint32_t acc[Terms::NACC];\n";
+  if (split)
+    os << "  static uint32_t park[32 * 32];\n"
+          "  qcut_lane_tile_split<Terms>(obs, qpd, nbq, ns, lane, acc, park + lane);\n";
+  else
+    os << "  qcut_lane_tile<Terms::NB, Terms>(obs, qpd, nbq, ns, lane, acc);\n";
+  os << "  for (int t = 0; t < Terms::T; ++t) odd_out[t] = (acc[t % Terms::NACC] >> (8 * (t / Terms::NACC))) & 0xFFu;\n"
         "  return Terms::T;\n"
         "}\n"
         "// run-time-mask engine, one lane of one tile (planes parked in a per-lane column)\n"
@@ -469,7 +560,10 @@ int jit_build(qcut_plan* plan, bool load) {
     jk.min_blocks = env_blocks ? std::atoi(env_blocks) : 0;
     const char* env_pf = std::getenv("QCUT_JIT_PREFETCH");
     const int prefetch = env_pf ? std::atoi(env_pf) : 0;
-    jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads, prefetch);
+    const char* env_split = std::getenv("QCUT_JIT_SPLIT");
+    const bool allow_split = !(env_split && *env_split && std::atoi(env_split) == 0);
+    jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads, prefetch,
+                                       allow_split, &jk.split);
     rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
   };
   std::atomic<size_t> next{0};
@@ -509,6 +603,11 @@ int jit_build(qcut_plan* plan, bool load) {
       jk.threads = 32 * warps;
       jk.min_blocks = 2;
       jk.smem_bytes = warps * (32 * (4 * jk.nb_obs + 1) + blocks * 32 * 32) * 4;
+      int dev = 0;
+      QCUT_CUDA(cudaGetDevice(&dev));
+      QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));
+    } else if (jk.split) {
+      jk.smem_bytes = (jk.threads / 32) * 32 * 32 * 4;  // one 32 x 32-word parking area per warp
       int dev = 0;
       QCUT_CUDA(cudaGetDevice(&dev));
       QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));
@@ -564,7 +663,9 @@ size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const
   if (!h_groups || group < 0 || group >= n_groups) return 0;
   const qcut_group_desc& gd = h_groups[group];
   if ((size_t)gd.mask_offset + (size_t)gd.n_terms * gd.nb_obs > mask_bytes) return 0;
-  const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, false, 256, 0);
+  const char* env_split = std::getenv("QCUT_JIT_SPLIT");
+  const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, false, 256, 0,
+                                                       !(env_split && *env_split && std::atoi(env_split) == 0), nullptr);
   if (src.empty()) return 0;
   if (buf && buf_len) {
     const size_t n = src.size() < buf_len - 1 ? src.size() : buf_len - 1;

@@ -442,6 +442,79 @@ QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __r
   }
 }
 
+// ---- term engine A', 8-byte rows, one 32x32 block at a time ("split") ----------------------------------
+// The all-at-once form above keeps both blocks of a step -- 64 bit-plane registers -- live through the whole XOR
+// network: with the packed counters that is 128 registers, 16 warps per SM, and the profile shows the warps
+// waiting on each other's POPC / load latency (issue slots 57 % busy).  Most terms of a real observable touch one
+// half of the row only (a term acts on a few neighbouring qubits), so the generator (jit.cu) sorts the terms into
+// block-0 terms, block-1 terms and cross terms, and this engine
+//   loads the 16 chunks once (x, z -> block 0 registers; y, w -> parked in the lane's private shared-memory column),
+//   transposes block 0, runs the block-0 terms and the block-0 half of every cross term (Terms::run0; the partial
+//   parity words of the cross terms stay in KEEP registers),
+//   fetches the parked words, transposes block 1 and finishes (Terms::run1).
+// Peak live registers: 32 planes + KEEP + counters, which lets 20-24 warps share an SM.
+template <class Terms, bool FULL>
+QCUT_DEV void qcut_split_step(const uint8_t* __restrict__ obs_s, const uint8_t* __restrict__ qpd_s, int nbq, int n,
+                              int lane, uint32_t* acc, uint32_t* __restrict__ park) {
+  typedef QcutGeo<8> G;
+  const QcutSrcGlobal src = {obs_s, qpd_s};
+  uint32_t a[1][32];
+  uint32_t qp[1];
+#pragma unroll
+  for (int k = 0; k < G::CHUNKS; ++k) {
+    qcut_u4 v = {0u, 0u, 0u, 0u};
+    if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
+    a[0][2 * k] = v.x;
+    a[0][2 * k + 1] = v.z;
+    park[(2 * k) * 32] = v.y;
+    park[(2 * k + 1) * 32] = v.w;
+  }
+  if (nbq == 1) {
+    uint32_t qraw[G::QRAW];
+    qcut_qpd_loads<8, FULL, QcutSrcGlobal>(src, n, lane, qraw);
+    qcut_qpd_planes<8>(qraw, qp);
+  } else {
+    qp[0] = 0;
+    qcut_qp_slow<8>(qpd_s, nbq, n, lane, qp);
+  }
+  uint32_t valid = 0xFFFFFFFFu;
+  if constexpr (!FULL) {
+    valid = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) valid |= (uint32_t)(qcut_shot_of<8>(j, 0, lane) < n) << j;
+    qp[0] &= valid;
+  }
+  qcut_transpose32(a[0]);
+  if constexpr (!FULL) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[0][i] &= valid;
+  }
+  uint32_t keep[Terms::NKEEP > 0 ? Terms::NKEEP : 1];
+  Terms::run0(a[0], qp[0], acc, keep);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) a[0][j] = park[j * 32];
+  qcut_transpose32(a[0]);
+  if constexpr (!FULL) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[0][i] &= valid;
+  }
+  Terms::run1(a[0], qp[0], acc, keep);
+}
+
+// park: this lane's column of the warp's 32 x 32-word parking area (park[j * 32], conflict free).
+template <class Terms>
+QCUT_DEV void qcut_lane_tile_split(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns,
+                                   int lane, uint32_t* acc, uint32_t* __restrict__ park) {
+  typedef QcutGeo<8> G;
+#pragma unroll
+  for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+  for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    if (n == G::STEP_SHOTS) qcut_split_step<Terms, true>(obs + (uint64_t)s0 * 8, qpd + (uint64_t)s0 * nbq, nbq, n, lane, acc, park);
+    else qcut_split_step<Terms, false>(obs + (uint64_t)s0 * 8, qpd + (uint64_t)s0 * nbq, nbq, n, lane, acc, park);
+  }
+}
+
 // ---- wide rows (9..32 bytes): rows staged through shared memory, bit-planes parked in shared memory ----
 // Up to 128 bit-planes do not fit the register file, so the blocks are transposed one at a time and the
 // planes are parked in shared memory ([plane][lane], conflict free); the generated term code then reads
@@ -637,6 +710,10 @@ QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long lo
     if (r < NACC && t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
   }
 }
+#endif  // !QCUT_HOST_EMU
+#if !defined(QCUT_HOST_EMU) && defined(QCUT_WITH_VARIANTS)
+// (experiments that measured slower than the default, DESIGN.md section 4: the generator defines QCUT_WITH_VARIANTS
+//  only when a plan asks for one of them, so NVRTC does not parse them otherwise)
 // ---- direct (HBM -> registers) tile loop with L2 prefetch one step ahead (device only) ---------------
 // cp.async.bulk.prefetch.L2 costs no registers and no shared memory: while the warp works on step s,
 // the copy engine pulls the bytes of step s+1 (or of the first step of the warp's next tile) into L2,

@@ -643,32 +643,11 @@ def gather_arrays(tables: HostTables, arrays: HostArrays, dst_ptr: int, n_thread
 # call, PCIe ceiling of the box 55 GB/s).  One rank per host: 292 ms with 256 MiB written with streaming stores
 # (qcut_stage_h2d does that for rings >= 64 MiB per call), 308 ms with 128 MiB / 326 ms with 64 or 256 MiB and
 # ordinary stores, 352 ms with 32 MiB (pieces too small for PCIe).  Several ranks on one host: the path is bound by
-# the host's memory bandwidth -- every shot byte is read from its BitArray, written to the ring and read again by
-# the DMA engine -- unless the ring stays in the caches: then only the first of the three passes touches DRAM.
-# Hence: 256 MiB alone on a host; with local peers each rank takes its share of HALF the last-level cache
-# (ordinary stores, so that the DMA engine finds the lines in the cache), cut into slots of >= 512 KiB.
-def _llc_bytes() -> int:
-    """Size of the last-level cache this process can count on (all L3 instances of the host), 32 MiB if unknown."""
-    total, seen = 0, set()
-    try:
-        base = "/sys/devices/system/cpu"
-        for cpu in os.listdir(base):
-            path = f"{base}/{cpu}/cache/index3"
-            if not cpu.startswith("cpu") or not cpu[3:].isdigit() or not os.path.isdir(path):
-                continue
-            with open(f"{path}/shared_cpu_list") as f:
-                key = f.read().strip()
-            if key in seen:
-                continue
-            seen.add(key)
-            with open(f"{path}/size") as f:
-                txt = f.read().strip().upper()
-            total += int(txt[:-1]) * {"K": 1 << 10, "M": 1 << 20, "G": 1 << 30}[txt[-1]] if txt[-1] in "KMG" else int(txt)
-    except (OSError, ValueError, KeyError):
-        total = 0
-    return total or (32 << 20)
-
-
+# the host's memory-copy ceiling -- every shot byte is read from its BitArray and written to the ring (then read by
+# the DMA engine).  Round 2 sweep with two ranks on a 24-core host whose copy ceiling (scripts/host_bw.py, 16
+# threads) is 60 GB/s: 64 MiB ring x 8 threads 30.3 GB/s per rank (= the ceiling), 16 MiB x 4 30.5, 8 MiB x 2 22.5,
+# 4 MiB x 2 20.1, 2 MiB x 1 11.4 -- a ring small enough to stay in the caches does NOT help (the copy itself is
+# the limit, not the DMA read), so the defaults stay: 256 MiB alone on a host, 64 MiB with local peers.
 def _local_peers() -> int:
     try:
         return max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
@@ -677,24 +656,13 @@ def _local_peers() -> int:
 
 
 def _default_staging_bytes() -> int:
-    peers = _local_peers()
-    if peers <= 1:
-        return 256 << 20
-    share = _llc_bytes() // (2 * peers)
-    return int(min(64 << 20, max(2 << 20, share))) & ~((1 << 20) - 1)
-
-
-def _default_staging_threads() -> int:
-    """Gather threads per feeder (two feeders).  Alone on a host 4 and 8 measured the same; with local peers the
-    ranks share the cores: two feeders x threads x peers should not exceed them."""
-    peers = _local_peers()
-    if peers <= 1:
-        return 8
-    return max(1, min(8, (os.cpu_count() or 8) // (2 * peers)))
+    return (256 if _local_peers() <= 1 else 64) << 20
 
 
 _STAGING_BYTES = int(os.environ.get("QCUT_STAGING_MB", "0") or 0) << 20 or _default_staging_bytes()
-_STAGING_THREADS = int(os.environ.get("QCUT_STAGING_THREADS", "0") or 0) or _default_staging_threads()
+# Gather threads per feeder (two feeders).  4 and 8 measured the same alone on a host; with two ranks on a 24-core
+# host 8 (64 MiB ring) and 4 (16 MiB) were the best of a sweep, 2 and 1 clearly worse.
+_STAGING_THREADS = int(os.environ.get("QCUT_STAGING_THREADS", "0") or 0) or 8
 _BLOCK_PUBS = 2048  # PUBs in the first staging block of a label (~1 ms of attribute walk); later blocks grow 4x
 
 
@@ -913,8 +881,10 @@ def plan_sharding(results_by_label: list, collections: list, n_coeffs: int, rank
         return D.Sharding("coefficients", 0, 1, 0, n_coeffs)
     lo, hi = D.coefficient_slice(n_coeffs, rank, world)
     plain = D.Sharding("coefficients", rank, world, lo, hi)
-    if any(isinstance(r, D.ShardedResult) for r in results_by_label) or n_coeffs == 0:
-        return plain  # every rank holds its own equal-count shard: nothing to balance, nothing to look at
+    if any(isinstance(r, D.ShardedResult) or hasattr(r, "quasi_dists") for r in results_by_label) or n_coeffs == 0:
+        # every rank holds its own equal-count shard / SamplerV1 quasi-distributions (no shot bytes): nothing to
+        # balance, nothing to look at
+        return plain
     groups = [len(c.groups) for c in collections]
     n_pubs = n_coeffs * sum(groups)
     if n_pubs > D.FULL_WALK_PUBS:

@@ -228,6 +228,11 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
 
   std::ostringstream os;
   if (staged || prefetch > 0) os << "#define QCUT_WITH_VARIANTS 1\n";
+  if (split) {
+    const char* env_ph = std::getenv("QCUT_JIT_SPLIT_PHASES");
+    const int phases = env_ph && *env_ph ? std::atoi(env_ph) : 1;
+    os << "#define QCUT_SPLIT_PHASES " << (phases == 2 || phases == 4 ? phases : 1) << "\n";
+  }
   os << kPrelude << "\n";
   os << terms.str();
   if (nb > 8) {

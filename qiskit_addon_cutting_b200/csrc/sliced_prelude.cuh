@@ -453,65 +453,105 @@ QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __r
 //   parity words of the cross terms stay in KEEP registers),
 //   fetches the parked words, transposes block 1 and finishes (Terms::run1).
 // Peak live registers: 32 planes + KEEP + counters, which lets 20-24 warps share an SM.
-template <class Terms, bool FULL>
-QCUT_DEV void qcut_split_step(const uint8_t* __restrict__ obs_s, const uint8_t* __restrict__ qpd_s, int nbq, int n,
-                              int lane, uint32_t* acc, uint32_t* __restrict__ park) {
+// Parking area accesses: volatile PTX so that the compiler cannot forward the stored words to the later loads in
+// registers (which would bring the 64 live registers back).
+#ifndef QCUT_HOST_EMU
+QCUT_DEV void qcut_park_store(uint32_t addr, uint32_t lo, uint32_t hi) {
+  asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+128], %2;" :: "r"(addr), "r"(lo), "r"(hi) : "memory");
+}
+QCUT_DEV uint32_t qcut_park_load(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+QCUT_DEV uint32_t qcut_park_addr(const uint32_t* park) { return (uint32_t)__cvta_generic_to_shared(park); }
+#else
+static uint32_t* qcut_park_base;
+QCUT_DEV uint32_t qcut_park_addr(uint32_t* park) { qcut_park_base = park; return 0; }
+QCUT_DEV void qcut_park_store(uint32_t addr, uint32_t lo, uint32_t hi) {
+  qcut_park_base[addr / 4] = lo;
+  qcut_park_base[addr / 4 + 32] = hi;
+}
+QCUT_DEV uint32_t qcut_park_load(uint32_t addr) { return qcut_park_base[addr / 4]; }
+#endif
+
+// Loads of one step: x, z -> rows of block 0 (registers); y, w -> rows of block 1, parked at byte offset 128 * row of
+// the lane's column; raw qpd bytes.  The 16 loads are issued in QCUT_SPLIT_PHASES groups, each group back to back
+// (no consumer between two loads of a group) and parked before the next group is issued: one group keeps the most
+// bytes in flight per warp but needs all 64 row registers for a moment, two groups never hold more than 48.
+#ifndef QCUT_SPLIT_PHASES
+#define QCUT_SPLIT_PHASES 1
+#endif
+template <bool FULL>
+QCUT_DEV void qcut_split_loads(const QcutSrcGlobal src, int n, int lane, uint32_t* a, uint32_t park, uint32_t* qraw,
+                               bool qpd_one_byte) {
   typedef QcutGeo<8> G;
-  const QcutSrcGlobal src = {obs_s, qpd_s};
-  uint32_t a[1][32];
-  uint32_t qp[1];
+  constexpr int PER = G::CHUNKS / QCUT_SPLIT_PHASES;
 #pragma unroll
-  for (int k = 0; k < G::CHUNKS; ++k) {
-    qcut_u4 v = {0u, 0u, 0u, 0u};
-    if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
-    a[0][2 * k] = v.x;
-    a[0][2 * k + 1] = v.z;
-    park[(2 * k) * 32] = v.y;
-    park[(2 * k + 1) * 32] = v.w;
-  }
-  if (nbq == 1) {
-    uint32_t qraw[G::QRAW];
-    qcut_qpd_loads<8, FULL, QcutSrcGlobal>(src, n, lane, qraw);
-    qcut_qpd_planes<8>(qraw, qp);
-  } else {
-    qp[0] = 0;
-    qcut_qp_slow<8>(qpd_s, nbq, n, lane, qp);
-  }
-  uint32_t valid = 0xFFFFFFFFu;
-  if constexpr (!FULL) {
-    valid = 0;
+  for (int ph = 0; ph < QCUT_SPLIT_PHASES; ++ph) {
+    uint32_t hi[2 * PER];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) valid |= (uint32_t)(qcut_shot_of<8>(j, 0, lane) < n) << j;
-    qp[0] &= valid;
-  }
-  qcut_transpose32(a[0]);
-  if constexpr (!FULL) {
+    for (int c = 0; c < PER; ++c) {
+      const int k = ph * PER + c;
+      qcut_u4 v = {0u, 0u, 0u, 0u};
+      if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
+      a[2 * k] = v.x;
+      a[2 * k + 1] = v.z;
+      hi[2 * c] = v.y;
+      hi[2 * c + 1] = v.w;
+    }
+    if (ph == 0 && qpd_one_byte) qcut_qpd_loads<8, FULL, QcutSrcGlobal>(src, n, lane, qraw);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a[0][i] &= valid;
+    for (int c = 0; c < PER; ++c) qcut_park_store(park + 256 * (ph * PER + c), hi[2 * c], hi[2 * c + 1]);
   }
-  uint32_t keep[Terms::NKEEP > 0 ? Terms::NKEEP : 1];
-  Terms::run0(a[0], qp[0], acc, keep);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) a[0][j] = park[j * 32];
-  qcut_transpose32(a[0]);
-  if constexpr (!FULL) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a[0][i] &= valid;
-  }
-  Terms::run1(a[0], qp[0], acc, keep);
 }
 
-// park: this lane's column of the warp's 32 x 32-word parking area (park[j * 32], conflict free).
+// park: this lane's column of the warp's 32 x 32-word parking area (row j at park[j * 32], conflict free).
 template <class Terms>
 QCUT_DEV void qcut_lane_tile_split(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns,
-                                   int lane, uint32_t* acc, uint32_t* __restrict__ park) {
+                                   int lane, uint32_t* acc, uint32_t* __restrict__ park_ptr) {
   typedef QcutGeo<8> G;
+  const uint32_t park = qcut_park_addr(park_ptr);
 #pragma unroll
   for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
   for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
     const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
-    if (n == G::STEP_SHOTS) qcut_split_step<Terms, true>(obs + (uint64_t)s0 * 8, qpd + (uint64_t)s0 * nbq, nbq, n, lane, acc, park);
-    else qcut_split_step<Terms, false>(obs + (uint64_t)s0 * 8, qpd + (uint64_t)s0 * nbq, nbq, n, lane, acc, park);
+    const bool full = n == G::STEP_SHOTS;
+    const uint8_t* __restrict__ qpd_s = qpd + (uint64_t)s0 * nbq;
+    const QcutSrcGlobal src = {obs + (uint64_t)s0 * 8, qpd_s};
+    uint32_t a[32];
+    uint32_t qp[1];
+    uint32_t qraw[G::QRAW];
+    if (full) qcut_split_loads<true>(src, n, lane, a, park, qraw, nbq == 1);
+    else qcut_split_loads<false>(src, n, lane, a, park, qraw, nbq == 1);
+    if (nbq == 1) {
+      qcut_qpd_planes<8>(qraw, qp);
+    } else {
+      qp[0] = 0;
+      qcut_qp_slow<8>(qpd_s, nbq, n, lane, qp);
+    }
+    uint32_t valid = 0xFFFFFFFFu;
+    if (!full) {  // rows past the end of the PUB hold bytes of the padding / next matrix: drop their shots
+      valid = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) valid |= (uint32_t)(qcut_shot_of<8>(j, 0, lane) < n) << j;
+      qp[0] &= valid;
+    }
+    qcut_transpose32(a);
+    if (!full) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] &= valid;
+    }
+    uint32_t keep[Terms::NKEEP > 0 ? Terms::NKEEP : 1];
+    Terms::run0(a, qp[0], acc, keep);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = qcut_park_load(park + 128 * j);
+    qcut_transpose32(a);
+    if (!full) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] &= valid;
+    }
+    Terms::run1(a, qp[0], acc, keep);
   }
 }
 

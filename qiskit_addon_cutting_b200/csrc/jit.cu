@@ -566,7 +566,9 @@ int jit_build(qcut_plan* plan, bool load) {
     const char* env_pf = std::getenv("QCUT_JIT_PREFETCH");
     const int prefetch = env_pf ? std::atoi(env_pf) : 0;
     const char* env_split = std::getenv("QCUT_JIT_SPLIT");
-    const bool allow_split = !(env_split && *env_split && std::atoi(env_split) == 0);
+    // off by default: measured slower on B200 (cfg4: 0.71 of HBM at 256x2, 0.60-0.66 with 3-5 CTAs per SM vs 0.76 for
+    // the all-at-once form -- the extra warps do not pay for the spills of the packed counters)
+    const bool allow_split = env_split && *env_split && std::atoi(env_split) != 0;
     jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads, prefetch,
                                        allow_split, &jk.split);
     rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
@@ -670,7 +672,7 @@ size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const
   if ((size_t)gd.mask_offset + (size_t)gd.n_terms * gd.nb_obs > mask_bytes) return 0;
   const char* env_split = std::getenv("QCUT_JIT_SPLIT");
   const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, false, 256, 0,
-                                                       !(env_split && *env_split && std::atoi(env_split) == 0), nullptr);
+                                                       env_split && *env_split && std::atoi(env_split) != 0, nullptr);
   if (src.empty()) return 0;
   if (buf && buf_len) {
     const size_t n = src.size() < buf_len - 1 ? src.size() : buf_len - 1;

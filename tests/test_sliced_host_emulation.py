@@ -135,3 +135,25 @@ def test_emulated_wide_row_kernel(lib, nbits, qbits, shots):
     assert covered.all(), "rows of 9..32 bytes must be covered by the specialised kernels"
     assert np.array_equal(got, want)
     del guarded
+
+
+@pytest.mark.parametrize("shots", [1, 1024, 1500, 4097, 6200])
+def test_emulated_split_engine_for_8_byte_rows(lib, monkeypatch, shots):
+    """The experimental one-block-at-a-time engine (QCUT_JIT_SPLIT=1; off by default, measured slower): block-local terms,
+    a few terms straddling the two halves of the row (their partial words are kept between the halves), identity."""
+    monkeypatch.setenv("QCUT_JIT_SPLIT", "1")
+    labels = []
+    for q in range(64):  # single-qubit terms on every qubit: 64 measured bits -> 8-byte rows
+        labels.append("".join("Z" if 63 - i == q else "I" for i in range(64)))
+    for a, b in ((3, 4), (30, 31), (31, 32), (28, 40), (33, 60), (62, 63), (0, 63)):  # pairs, three of them cross
+        labels.append("".join("Z" if 63 - i in (a, b) else "I" for i in range(64)))
+    labels.append("I" * 64)
+    observables = {"A": PauliList(labels)}
+    results = _cases.make_results(observables, 1, shots, 3, seed=shots)
+    tables, data, want = _stage_host(results, [(1.0, WeightType.EXACT)], observables)
+    source = _lib.generate_source(tables.groups, tables.masks, 0)
+    assert "SPLIT = 1" in source and "NKEEP = 3" in source and "qcut_lane_tile_split" in source
+    got, covered = _host_emu.emulate_tallies(tables, data, "jit")
+    assert covered.all() and np.array_equal(got, want)
+    monkeypatch.delenv("QCUT_JIT_SPLIT")
+    assert "qcut_lane_tile_split<Terms>" not in _lib.generate_source(tables.groups, tables.masks, 0).split("extern \"C\"", 1)[1]

@@ -469,8 +469,16 @@ def measure(args, name: str, *, steps: int, warmup: int, e2e_steps: int, cpu_sec
             pairs = W.coefficient_pairs(tables.coeffs)
             group = None
         ceiling = host_copy_ceiling() if rank == 0 else None
+        t = time.perf_counter()
         got = reconstruct_expectation_values(results, pairs, w.observables, process_group=group)  # warm-up (pinned buffer, plan cache)
         torch.cuda.synchronize()
+        first = time.perf_counter() - t
+        if world == 1 and first < 0.02:
+            # a call of a millisecond or less: average over enough calls (~0.3 s) for a stable figure
+            got = reconstruct_expectation_values(results, pairs, w.observables)
+            t = time.perf_counter()
+            got = reconstruct_expectation_values(results, pairs, w.observables)
+            e2e_steps = int(min(300, max(e2e_steps, 0.3 / max(time.perf_counter() - t, 1e-5))))
         if world > 1:
             dist.barrier()
         t = time.perf_counter()

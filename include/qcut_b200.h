@@ -111,6 +111,7 @@ int qcut_device_count(void);
  * QCUT_CACHE_DIR="" disables the cache. */
 #define QCUT_PLAN_NO_JIT 1u
 #define QCUT_PLAN_GENERIC_ONLY 2u
+#define QCUT_PLAN_ASYNC_JIT 8u /* qcut_plan_create returns at once: NVRTC runs on a background thread and, until it is done, schedules are served by the ahead-of-time kernels (run-time masks / generic) -- no cold start */
 #define QCUT_PLAN_STAGED 4u /* specialised kernels prefetch each step through shared memory with bulk async copies (UBLKCP + mbarrier) instead of loading straight from HBM; measured slower on B200 for this ALU-issue-bound kernel, kept for experiments */
 #define QCUT_MAX_JIT_KERNELS 8
 int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
@@ -120,6 +121,11 @@ int qcut_plan_group_kernel(const qcut_plan* plan, int group);
 /* Copies the generated CUDA source of specialised kernel `kernel` (>= 2), NUL terminated, into
  * buf; returns the full length needed (0 if there is no such kernel).  For inspection only. */
 size_t qcut_plan_source(const qcut_plan* plan, int kernel, char* buf, size_t buf_len);
+/* State of the specialised kernels: 0 none requested, 1 being compiled (QCUT_PLAN_ASYNC_JIT), 2 ready, -1 failed (the
+ * plan keeps working on the ahead-of-time kernels; qcut_plan_wait reports the error).  qcut_plan_wait blocks until
+ * the background compilation has finished. */
+int qcut_plan_jit_state(const qcut_plan* plan);
+int qcut_plan_wait(qcut_plan* plan);
 
 /* ---- schedule -----------------------------------------------------------------------------------
  * Copies the PUB table to HBM and cuts every PUB into tiles of QCUT_TILE_SHOTS consecutive shots,

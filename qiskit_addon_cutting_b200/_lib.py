@@ -25,6 +25,7 @@ REDUCE_SINGLE_SLOT, REDUCE_SEQUENTIAL = 1, 2
 PLAN_NO_JIT = 1
 PLAN_GENERIC_ONLY = 2
 PLAN_STAGED = 4
+PLAN_ASYNC_JIT = 8
 KERNEL_GENERIC, KERNEL_SLICED_RT, KERNEL_JIT0 = 0, 1, 2
 
 
@@ -87,6 +88,8 @@ SIGNATURES = {
     "qcut_plan_destroy": (None, [_VP]),
     "qcut_plan_group_kernel": (_INT, [_VP, _INT]),
     "qcut_plan_source": (_SZ, [_VP, _INT, C.c_char_p, _SZ]),
+    "qcut_plan_jit_state": (_INT, [_VP]),
+    "qcut_plan_wait": (_INT, [_VP]),
     "qcut_schedule_create": (_INT, [_VP, _VP, _I64, C.POINTER(_VP)]),
     "qcut_schedule_destroy": (None, [_VP]),
     "qcut_schedule_num_tiles": (_I64, [_VP]),

@@ -181,6 +181,7 @@ int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_
     dev.n_words = (gd.nb_obs + 3) / 4;
     dev.word_offset = (uint32_t)words.size();
     dev.kernel = (!(flags & QCUT_PLAN_GENERIC_ONLY) && sliced_rt_supports(gd.nb_obs)) ? KERNEL_SLICED_RT : KERNEL_GENERIC;
+    plan->fallback_kernel.push_back(dev.kernel);
     for (uint32_t t = 0; t < gd.n_terms; ++t) {
       const uint8_t* row = h_masks + gd.mask_offset + (size_t)t * gd.nb_obs;
       for (uint32_t w = 0; w < dev.n_words; ++w) {
@@ -191,12 +192,16 @@ int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_
     }
   }
 
-  if (!(flags & (QCUT_PLAN_NO_JIT | QCUT_PLAN_GENERIC_ONLY))) {
+  const bool want_jit = !(flags & (QCUT_PLAN_NO_JIT | QCUT_PLAN_GENERIC_ONLY));
+  if (want_jit) {
     assign_jit_kernels(plan);
-    const int rc = jit_build(plan, true);
-    if (rc != QCUT_OK) {
-      qcut_plan_destroy(plan);
-      return rc;
+    if (!(flags & QCUT_PLAN_ASYNC_JIT)) {
+      const int rc = jit_build(plan, true);
+      if (rc != QCUT_OK) {
+        qcut_plan_destroy(plan);
+        return rc;
+      }
+      plan->jit_state.store(plan->jit.empty() ? qcut_plan::JIT_NONE : qcut_plan::JIT_READY, std::memory_order_release);
     }
   }
 
@@ -216,12 +221,35 @@ int qcut_plan_create(const qcut_group_desc* h_groups, int n_groups, const uint8_
     err = cudaMemcpy(plan->d_mask_words, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     if (err != cudaSuccess) return fail(err, "cudaMemcpy(mask words)");
   }
+  if (want_jit && (flags & QCUT_PLAN_ASYNC_JIT) && !plan->jit.empty()) {
+    // NVRTC + module loading on a background thread; until it is done the ahead-of-time kernels serve every group
+    int device = 0;
+    cudaGetDevice(&device);
+    plan->jit_state.store(qcut_plan::JIT_PENDING, std::memory_order_release);
+    plan->jit_thread = std::thread([plan, device]() {
+      int rc = cudaSetDevice(device) == cudaSuccess ? jit_build(plan, true) : QCUT_ERR_CUDA;
+      if (rc != QCUT_OK) plan->jit_error = plan->jit_cancel.load() ? "cancelled" : qcut_last_error();
+      plan->jit_state.store(rc == QCUT_OK ? qcut_plan::JIT_READY : qcut_plan::JIT_FAILED, std::memory_order_release);
+    });
+  }
   *out_plan = plan;
+  return QCUT_OK;
+}
+
+int qcut_plan_jit_state(const qcut_plan* plan) { return plan ? plan->jit_state.load(std::memory_order_acquire) : 0; }
+
+int qcut_plan_wait(qcut_plan* plan) {
+  if (!plan) return set_error("qcut_plan_wait: plan is NULL"), QCUT_ERR_INVALID;
+  if (plan->jit_thread.joinable()) plan->jit_thread.join();
+  if (plan->jit_state.load(std::memory_order_acquire) == qcut_plan::JIT_FAILED)
+    return set_error("background specialisation failed: " + plan->jit_error), QCUT_ERR_JIT;
   return QCUT_OK;
 }
 
 void qcut_plan_destroy(qcut_plan* plan) {
   if (!plan) return;
+  plan->jit_cancel.store(true);  // a compilation in flight stops after the kernel it is working on
+  if (plan->jit_thread.joinable()) plan->jit_thread.join();
   jit_release(plan);
   for (int i = 0; i < qcut_plan::kSideStreams; ++i) {
     if (plan->side[i]) cudaStreamDestroy(plan->side[i]);
@@ -235,11 +263,13 @@ void qcut_plan_destroy(qcut_plan* plan) {
 
 int qcut_plan_group_kernel(const qcut_plan* plan, int group) {
   if (!plan || group < 0 || group >= plan->n_groups) return set_error("qcut_plan_group_kernel: bad group"), QCUT_ERR_INVALID;
-  return (int)plan->groups_dev[group].kernel;
+  return (int)plan->kernel_for(group, plan->jit_state.load(std::memory_order_acquire) != qcut_plan::JIT_PENDING &&
+                                          plan->jit_state.load(std::memory_order_acquire) != qcut_plan::JIT_FAILED);
 }
 
 size_t qcut_plan_source(const qcut_plan* plan, int kernel, char* buf, size_t buf_len) {
   if (!plan || kernel < (int)KERNEL_JIT0 || kernel >= plan->n_kernels()) return 0;
+  if (plan->jit_state.load(std::memory_order_acquire) == qcut_plan::JIT_PENDING) return 0;  // still being written
   const std::string& src = plan->jit[kernel - KERNEL_JIT0].source;
   if (buf && buf_len) {
     const size_t n = std::min(buf_len - 1, src.size());
@@ -321,11 +351,15 @@ int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int
   if (!plan || n_pubs < 0 || (n_pubs > 0 && !h_pubs)) return set_error("qcut_schedule_create: bad argument"), QCUT_ERR_INVALID;
   if (n_pubs >= (int64_t)1 << 32) return set_error("qcut_schedule_create: more than 2^32 PUBs"), QCUT_ERR_INVALID;
   const int nk = plan->n_kernels();
+  // specialised kernels only if they are there now (a background compilation may still be running)
+  const int jit_state = plan->jit_state.load(std::memory_order_acquire);
+  const bool use_jit = jit_state != qcut_plan::JIT_PENDING && jit_state != qcut_plan::JIT_FAILED;
   // Tiles are listed kernel by kernel and, inside a kernel, variant by variant (PUB order within).
   constexpr int64_t kMaxVariants = 64;
   auto key_of = [&](const qcut_pub_desc& pd) {
     const GroupDev& gd = plan->groups_dev[pd.group];
-    return (int64_t)gd.kernel * kMaxVariants + std::min<int64_t>(gd.variant, kMaxVariants - 1);
+    const int64_t kernel = plan->kernel_for((int)pd.group, use_jit);
+    return kernel * kMaxVariants + (kernel >= (int64_t)KERNEL_JIT0 ? std::min<int64_t>(gd.variant, kMaxVariants - 1) : 0);
   };
   std::vector<int64_t> count((size_t)nk * kMaxVariants + 1, 0);
   std::vector<int64_t> bytes((size_t)nk, 0);
@@ -337,13 +371,14 @@ int qcut_schedule_create(const qcut_plan* plan, const qcut_pub_desc* h_pubs, int
     }
     const int64_t tiles = ((int64_t)h_pubs[p].shots + QCUT_TILE_SHOTS - 1) / QCUT_TILE_SHOTS;
     count[(size_t)key_of(h_pubs[p]) + 1] += tiles;
-    bytes[(size_t)plan->groups_dev[h_pubs[p].group].kernel] +=
+    bytes[(size_t)plan->kernel_for((int)h_pubs[p].group, use_jit)] +=
         (int64_t)h_pubs[p].shots * ((int64_t)plan->groups[h_pubs[p].group].nb_obs + h_pubs[p].nb_qpd);
   }
   for (size_t k = 0; k + 1 < count.size(); ++k) count[k + 1] += count[k];
   qcut_schedule* sch = new (std::nothrow) qcut_schedule();
   if (!sch) return set_error("qcut_schedule_create: out of host memory"), QCUT_ERR_NOMEM;
   sch->n_pubs = n_pubs;
+  sch->use_jit = use_jit;
   sch->n_tiles = count.back();
   sch->kernel_bytes = bytes;
   sch->kernel_tile_begin.resize((size_t)nk + 1);

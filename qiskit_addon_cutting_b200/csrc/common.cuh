@@ -4,8 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "qcut_b200.h"
@@ -70,6 +72,18 @@ struct qcut_plan {
   uint32_t* d_mask_words = nullptr;        // little-endian words assembled from the byte rows
   std::vector<qcut::JitKernel> jit;        // kernel id = KERNEL_JIT0 + index
   int n_kernels() const { return (int)qcut::KERNEL_JIT0 + (int)jit.size(); }
+  // Ahead-of-time kernel of every group (run-time-mask or generic): what serves a group whose specialised kernel
+  // is not (yet) there.  With QCUT_PLAN_ASYNC_JIT the NVRTC work runs on `jit_thread`; a schedule uses the
+  // specialised kernels only if they were ready when it was created (jit_state, acquire/release).
+  enum : int { JIT_NONE = 0, JIT_PENDING = 1, JIT_READY = 2, JIT_FAILED = -1 };
+  std::vector<uint32_t> fallback_kernel;
+  std::atomic<int> jit_state{JIT_NONE};
+  std::atomic<bool> jit_cancel{false};
+  std::thread jit_thread;
+  std::string jit_error;
+  uint32_t kernel_for(int group, bool use_jit) const {
+    return use_jit ? groups_dev[(size_t)group].kernel : fallback_kernel[(size_t)group];
+  }
   // Side streams of qcut_tally_launch (created on first use, used under `side_mutex`): the K1 kernels of one
   // launch write disjoint tallies, so they are spread over streams and the ramp of one overlaps the tail of another.
   static constexpr int kSideStreams = 3;
@@ -92,4 +106,5 @@ struct qcut_schedule {
   // draining the device (the descriptors are recycled once that event has completed)
   mutable cudaStream_t last_stream = nullptr;
   mutable bool launched = false;
+  bool use_jit = true;  // tiles were listed for the specialised kernels (else for the ahead-of-time ones)
 };

@@ -545,6 +545,11 @@ int jit_build(qcut_plan* plan, bool load) {
   std::vector<std::string> errors(n);
   auto work = [&](size_t i) {
     JitKernel& jk = plan->jit[i];
+    if (plan->jit_cancel.load()) {  // the plan is being destroyed while its background compilation runs
+      rcs[i] = QCUT_ERR_JIT;
+      errors[i] = "cancelled";
+      return;
+    }
     if (!jk.variants.empty()) {
       std::vector<const qcut_group_desc*> gds;
       for (int g : jk.variants) gds.push_back(&plan->groups[g]);

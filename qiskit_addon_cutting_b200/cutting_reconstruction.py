@@ -181,7 +181,8 @@ def reconstruct_expectation_values(
         if all(v1):
             out = quasi.reconstruct_v1(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, sequential=literal)
         else:
-            out = engine.stage_v2(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, rounding=rounding).run()
+            out = engine.stage_v2(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, rounding=rounding,
+                                  public_call=True).run()
         return list(out.cpu().numpy())
 
     # ---- sharded over the ranks of the process group: every rank makes the same call -----------------
@@ -210,7 +211,7 @@ def reconstruct_expectation_values(
         batch = None
         try:
             batch = engine.stage_v2_pieces(result_list, collection_list, coeffs, n_obs, rank, world,
-                                           collected=sharding.collected)
+                                           collected=sharding.collected, public_call=True)
         except Exception as exc:  # noqa: BLE001
             error = exc
         if batch is not None:
@@ -228,7 +229,8 @@ def reconstruct_expectation_values(
                                                     sequential=literal)
                     else:
                         part = engine.stage_v2(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs,
-                                               collected=sharding.collected or None, rounding=rounding).run()
+                                               collected=sharding.collected or None, rounding=rounding,
+                                               public_call=True).run()
                     out = torch.zeros(n_obs + 1, dtype=torch.float64, device="cuda")
                     out[:n_obs] = part
             except Exception as exc:  # noqa: BLE001

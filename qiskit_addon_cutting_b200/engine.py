@@ -83,6 +83,15 @@ class Plan:
     def kernel_of(self, group: int) -> int:
         return _lib.load().qcut_plan_group_kernel(self.handle, group)
 
+    def jit_state(self) -> int:
+        """0: no specialised kernels requested, 1: being compiled in the background, 2: ready, -1: failed."""
+        return _lib.load().qcut_plan_jit_state(self.handle)
+
+    def wait(self) -> "Plan":
+        """Block until a background compilation (``PLAN_ASYNC_JIT``) has finished."""
+        check(_lib.load().qcut_plan_wait(self.handle), "qcut_plan_wait")
+        return self
+
     def kernels(self) -> list[int]:
         return [self.kernel_of(g) for g in range(len(self.groups))]
 
@@ -108,14 +117,24 @@ _plan_cache: dict = {}
 _plan_lock = threading.Lock()
 
 
-def get_plan(groups: np.ndarray, masks: np.ndarray, *, flags: int = 0) -> Plan:
+_SYNC_JIT = os.environ.get("QCUT_PLAN_SYNC", "0") not in ("0", "", "off")
+# Calls that stage less than this are launch bound whatever kernel runs (cfg1: 11.6 us specialised vs 14.0 us with
+# run-time masks; cfg2: 19.9 vs 24.8 us): they use the ahead-of-time kernels and never invoke NVRTC (a 1 s cold start).
+_SMALL_CALL_BYTES = 64 << 20
+
+
+def get_plan(groups: np.ndarray, masks: np.ndarray, *, flags: int = 0, background: bool = False) -> Plan:
+    """The plan for these groups (cached per device and mask content).  ``background``: if the plan has to be
+    created, its NVRTC specialisation runs on a background thread (``QCUT_PLAN_ASYNC_JIT``) and the call is served
+    by the ahead-of-time kernels until it is ready -- no cold start; ``QCUT_PLAN_SYNC=1`` switches that off."""
     key = (torch.cuda.current_device(), flags, groups.tobytes(), masks.tobytes())
     with _plan_lock:
         plan = _plan_cache.get(key)
         if plan is None:
             if len(_plan_cache) >= 16:
                 _plan_cache.pop(next(iter(_plan_cache)))
-            plan = _plan_cache[key] = Plan(groups, masks, flags=flags)
+            create = flags | (_lib.PLAN_ASYNC_JIT if background and not _SYNC_JIT else 0)
+            plan = _plan_cache[key] = Plan(groups, masks, flags=create)
         return plan
 
 
@@ -271,7 +290,7 @@ class DeviceBatch:
     """One rank's share of a reconstruction, resident in HBM."""
 
     def __init__(self, tables: HostTables, data, *, flags: int = 0, k1_pubs: np.ndarray | None = None,
-                 rounding: str = "exact"):
+                 rounding: str = "exact", public_call: bool = False):
         """``k1_pubs`` (tally-table sharding): the PUB pieces THIS rank tallies -- descriptors with this rank's
         data offsets and shot counts but the global ``tally_offset`` -- while ``tables.pubs`` stays the complete
         table the product/sum kernel reads after the tally table has been all-reduced.
@@ -286,7 +305,11 @@ class DeviceBatch:
         self.tables = tables
         if k1_pubs is None:
             k1_pubs = tables.k1_pubs
-        self.plan = get_plan(tables.groups, tables.masks, flags=flags)
+        if public_call and flags == 0 and tables.data_bytes < _SMALL_CALL_BYTES and not _SYNC_JIT:
+            flags = _lib.PLAN_NO_JIT  # launch-bound call: ahead-of-time kernels, no NVRTC at all
+        self.plan = get_plan(tables.groups, tables.masks, flags=flags, background=public_call)
+        if not public_call:
+            self.plan.wait()  # resident / benchmark use: always the specialised kernels
         self.schedule = Schedule(self.plan, tables.pubs if k1_pubs is None else k1_pubs)
         self.data = data
         small = [tables.labels, tables.lookup_start, tables.lookup, tables.coeffs]
@@ -765,7 +788,8 @@ def _stage_simple(tables: HostTables, arrays: HostArrays) -> torch.Tensor:
 
 
 def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
-             *, flags: int = 0, collected: dict | None = None, rounding: str = "exact") -> DeviceBatch:
+             *, flags: int = 0, collected: dict | None = None, rounding: str = "exact",
+             public_call: bool = False) -> DeviceBatch:
     """Stage the PUBs of coefficient range ``[i_lo, i_hi)`` of every label into HBM.
 
     Large inputs: the PUBs are walked block by block (``csrc/pyhelper.c``); background threads hand every walked
@@ -784,7 +808,7 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
             with _staging_lock(torch.cuda.current_device()):
                 data = _stage_simple(tables, arrays)
             t_staged = time.perf_counter()
-            batch = DeviceBatch(tables, data, flags=flags, rounding=rounding)
+            batch = DeviceBatch(tables, data, flags=flags, rounding=rounding, public_call=public_call)
             batch.keepalive = arrays.keep
             last_stage_trace = {"walk_s": t_walked - t_start, "stage_s": t_staged - t_walked,
                                 "tables_s": time.perf_counter() - t_staged, "path": "simple", "dedup": tables.dedup}
@@ -802,7 +826,7 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
         # plan lookup / schedule upload proceed while the last blocks are still in flight
         t_walked = time.perf_counter()
         try:
-            batch = DeviceBatch(tables, stager, flags=flags, rounding=rounding)
+            batch = DeviceBatch(tables, stager, flags=flags, rounding=rounding, public_call=public_call)
         finally:
             t_batch = time.perf_counter()
             stager.finish(raise_errors=False)
@@ -817,7 +841,7 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
 
 
 def stage_v2_pieces(results_by_label: list, collections: list, coeffs: np.ndarray, n_obs: int, rank: int,
-                    world: int, *, flags: int = 0, collected: dict | None = None) -> DeviceBatch:
+                    world: int, *, flags: int = 0, collected: dict | None = None, public_call: bool = False) -> DeviceBatch:
     """Tally-table sharding (``distributed`` module docstring): every rank describes ALL PUBs (descriptors only),
     stages the bytes of its own byte-balanced piece of the flattened (label, PUB, shot range) list and tallies it
     into the global tally table."""
@@ -861,7 +885,7 @@ def stage_v2_pieces(results_by_label: list, collections: list, coeffs: np.ndarra
             if stager.error is not None:
                 raise stager.error
             data = stager
-    batch = DeviceBatch(tables, data, flags=flags, k1_pubs=k1)
+    batch = DeviceBatch(tables, data, flags=flags, k1_pubs=k1, public_call=public_call)
     batch.keepalive = arrays.keep
     return batch
 

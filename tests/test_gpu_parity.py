@@ -307,3 +307,55 @@ def test_reference_rounding_for_every_row_width_and_many_tuples(lib, monkeypatch
     assert np.max(np.abs(np.array(reconstruct_expectation_values(results, coefficients, observables)) - want)) <= 1e-12
     with pytest.raises(ValueError):
         reconstruct_expectation_values(results, coefficients, observables, rounding="fast")
+
+
+def test_background_specialisation_has_no_cold_start(lib, monkeypatch, tmp_path):
+    """Public calls create their plan with QCUT_PLAN_ASYNC_JIT: NVRTC runs on a background thread and the call is
+    served by the ahead-of-time kernels meanwhile -- same tallies, same expectation values, no wait for the compiler."""
+    import time
+
+    monkeypatch.setenv("QCUT_CACHE_DIR", str(tmp_path))  # empty kernel cache: a real cold start
+    monkeypatch.setattr(engine, "_SMALL_CALL_BYTES", 0)   # (small calls would not use NVRTC at all)
+    rng = np.random.default_rng(20251)
+    observables = {"A": _cases.random_paulis(rng, 40, 64, 1, 3, "Z"), "B": _cases.random_paulis(rng, 40, 60, 1, 3, "Z")}
+    coefficients = _cases.random_coefficients(rng, 6)
+    results = _cases.make_results(observables, 6, 300, 2, seed=5)
+    want = _hex(oracle.reconstruct_exact(results, coefficients, observables))
+    labels = list(observables)
+    colls = [ObservableCollection(observables[k]) for k in labels]
+    coeffs = np.array([c for c, _ in coefficients])
+    t0 = time.perf_counter()
+    batch = engine.stage_v2([results[k] for k in labels], colls, coeffs, 0, 6, 40, public_call=True)
+    first = _hex(batch.run().cpu().numpy())
+    first_s = time.perf_counter() - t0
+    state_at_first_call = batch.plan.jit_state()
+    kernels_first = set(batch.plan.kernels()) if state_at_first_call == 1 else None
+    assert first == want
+    batch.plan.wait()
+    waited_s = time.perf_counter() - t0
+    assert batch.plan.jit_state() == 2 and max(batch.plan.kernels()) >= _lib.KERNEL_JIT0
+    assert _hex(reconstruct_expectation_values(results, coefficients, observables)) == want  # now on the specialised kernels
+    if kernels_first is not None:  # the compiler was still running when the first call returned
+        assert max(kernels_first) <= _lib.KERNEL_SLICED_RT
+    print(f"\\nfirst call {1e3 * first_s:.1f} ms (jit state {state_at_first_call}), specialised kernels ready after {waited_s:.2f} s")
+    # a plan destroyed while its compilation is in flight stops the compiler and does not hang
+    groups = batch.tables.groups.copy()
+    masks = batch.tables.masks.copy()
+    masks[0] ^= 1  # another mask set -> another compilation
+    monkeypatch.setenv("QCUT_CACHE_DIR", str(tmp_path / "other"))
+    t0 = time.perf_counter()
+    plan = engine.Plan(groups, masks, flags=_lib.PLAN_ASYNC_JIT)
+    created_s = time.perf_counter() - t0
+    del plan
+    assert created_s < 0.5, "plan creation must not wait for NVRTC"
+
+
+def test_small_public_calls_never_invoke_nvrtc(lib):
+    """Launch-bound calls (less than 64 MiB staged) run on the ahead-of-time kernels: nothing to compile."""
+    results, coefficients, observables = _cases.SMALL_CASES["heavy_hex"]()
+    labels = list(observables)
+    colls = [ObservableCollection(observables[k]) for k in labels]
+    coeffs = np.array([c for c, _ in coefficients])
+    batch = engine.stage_v2([results[k] for k in labels], colls, coeffs, 0, len(coeffs), len(observables["A"]), public_call=True)
+    assert batch.plan.jit_state() == 0 and max(batch.plan.kernels()) <= _lib.KERNEL_SLICED_RT
+    assert _hex(batch.run().cpu().numpy()) == _hex(oracle.reconstruct_exact(results, coefficients, observables))

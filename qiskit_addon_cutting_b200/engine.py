@@ -326,6 +326,23 @@ class DeviceBatch:
         self.tally_launches = 0
         self.expvals = None  # fp64 per-(PUB, term) expectation values of the reference-rounding mode
 
+    @classmethod
+    def from_skeleton(cls, skel: "_Skeleton", data: torch.Tensor, coeffs_dev: torch.Tensor, tables: HostTables,
+                      rounding: str) -> "DeviceBatch":
+        """A batch that shares everything layout-dependent (plan, schedule, uploaded tables) with earlier calls of the
+        same shape; only the shot bytes, the coefficients (staged behind the shot bytes) and the outputs are its own."""
+        self = cls.__new__(cls)
+        self.rounding, self.tables, self.plan, self.schedule, self.data = rounding, tables, skel.plan, skel.schedule, data
+        self.labels, self.lookup_start, self.lookup, self.coeffs = skel.labels, skel.lookup_start, skel.lookup, coeffs_dev
+        self.k2_pubs = None
+        self.tallies = torch.empty(tables.n_tallies + 1, dtype=torch.int64, device="cuda")
+        self.out = torch.empty(tables.n_obs + 1, dtype=torch.float64, device="cuda")
+        self.workspace = torch.empty(skel.workspace_bytes, dtype=torch.uint8, device="cuda")
+        self.tally_launches = 0
+        self.expvals = None
+        self._single_slot = skel.single_slot
+        return self
+
     def launch_tally(self) -> int:
         """K1 on the current stream: exact int64 sign tallies of every (PUB, term).  Returns #kernels launched."""
         n = C.c_int(0)
@@ -361,7 +378,10 @@ class DeviceBatch:
         """K2 on the current stream: this rank's partial ``out[k]``.  Returns #kernels launched (2)."""
         t = self.tables
         literal = self.rounding == "reference"
-        flags = (_lib.REDUCE_SINGLE_SLOT if t.single_slot else 0) | (_lib.REDUCE_SEQUENTIAL if literal else 0)
+        single_slot = getattr(self, "_single_slot", None)
+        if single_slot is None:
+            single_slot = self._single_slot = t.single_slot
+        flags = (_lib.REDUCE_SINGLE_SLOT if single_slot else 0) | (_lib.REDUCE_SEQUENTIAL if literal else 0)
         fn = _lib.load().qcut_reduce_expvals_launch if literal else _lib.load().qcut_reduce_launch
         check(
             fn(
@@ -768,23 +788,139 @@ _SIMPLE_BYTES = 64 << 20      # ... and staged by one gather + one H2D copy if i
 _copy_done: dict[int, torch.cuda.Event] = {}  # per device: last H2D copy out of the pinned buffer
 
 
-def _stage_simple(tables: HostTables, arrays: HostArrays) -> torch.Tensor:
+_PIPELINE_FROM = 4 << 20      # simple path: from this size on the gather and the H2D copy are pipelined in 2 MiB pieces
+
+
+def _stage_simple(tables: HostTables, arrays: HostArrays, extra: np.ndarray | None = None) -> torch.Tensor:
     """Small inputs: gather every borrowed buffer into the pinned buffer, ONE host-to-device copy on the current
-    stream.  No threads are started and nothing is pipelined: for the tutorial-sized calls the pipeline's fixed
-    costs (two feeder threads, a ring, one event per slot) were the larger part of the call."""
+    stream (no threads, nothing pipelined: for tutorial-sized calls the pipeline's fixed costs were the larger part
+    of the call).  From 4 MiB on, ``qcut_stage_h2d`` gathers 2 MiB pieces on four threads and copies each as soon as
+    it is complete.  ``extra`` (the coefficients of a cached layout) travels behind the shot bytes, at
+    ``_align(data_bytes + DATA_SLACK)``, in the same copy."""
     dev = torch.cuda.current_device()
     n = tables.data_bytes
-    pinned = _pinned_buffer(max(n, 1 << 20))
+    extra_off = _align(n + _lib.DATA_SLACK)
+    total = extra_off + (extra.nbytes if extra is not None else 0)
+    pinned = _pinned_buffer(max(total, 8 << 20))
     done = _copy_done.get(dev)
     if done is not None:
         done.synchronize()  # a previous call's copy may still be reading the pinned buffer
-    gather_arrays(tables, arrays, pinned.data_ptr(), n_threads=1 if n <= (4 << 20) else 8)
-    data = torch.empty(n + _lib.DATA_SLACK, dtype=torch.uint8, device="cuda")
-    data[:n].copy_(pinned[:n], non_blocking=True)
+    data = torch.empty(max(total, n + _lib.DATA_SLACK), dtype=torch.uint8, device="cuda")
+    if n >= _PIPELINE_FROM and len(arrays):
+        check(
+            _lib.load().qcut_stage_h2d(_lib.np_ptr(arrays.src), _lib.np_ptr(arrays.nbytes), _lib.np_ptr(arrays.dst), len(arrays),
+                                       pinned.data_ptr(), 8 << 20, data.data_ptr(), 4, _stream_ptr()),
+            "qcut_stage_h2d",
+        )  # returns when the bytes have left the pinned pieces
+        if extra is not None:
+            data[extra_off: total].copy_(torch.from_numpy(extra.view(np.uint8).reshape(-1)), non_blocking=False)
+        return data
+    gather_arrays(tables, arrays, pinned.data_ptr(), n_threads=1)
+    if extra is not None:
+        np.frombuffer((C.c_uint8 * extra.nbytes).from_address(pinned.data_ptr() + extra_off), dtype=np.uint8)[:] = \
+            extra.view(np.uint8).reshape(-1)
+        data[:total].copy_(pinned[:total], non_blocking=True)
+    else:
+        data[:n].copy_(pinned[:n], non_blocking=True)
     ev = _copy_done.get(dev) or torch.cuda.Event()
     ev.record()
     _copy_done[dev] = ev
     return data
+
+
+@dataclass
+class _Skeleton:
+    """Everything about a small call that depends only on its LAYOUT (observable groups, PUB shapes): repeated calls
+    of one shape -- the tutorial loop, a sweep over circuits of one family -- skip table building, the schedule upload
+    and four small copies, and stage their coefficients behind the shot bytes."""
+
+    tables: HostTables
+    nbytes: np.ndarray
+    dst: np.ndarray
+    plan: Plan
+    schedule: Schedule
+    labels: torch.Tensor
+    lookup_start: torch.Tensor
+    lookup: torch.Tensor
+    workspace_bytes: int
+    single_slot: bool
+    collections: list  # keeps the ids in the signature unique
+
+
+_skeletons: dict = {}
+_skeleton_lock = threading.Lock()
+_SKELETON_CACHE = os.environ.get("QCUT_LAYOUT_CACHE", "1") not in ("0", "", "off")
+
+
+def _stage_small(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
+                 flags: int, rounding: str, public_call: bool, t_start: float):
+    """The simple path with the layout cache.  Returns a DeviceBatch, or None when the call is not small after all
+    (more than ``_SIMPLE_BYTES``), in which case ``walked`` has been consumed for nothing but a few microseconds."""
+    global last_stage_trace
+    dev = torch.cuda.current_device()
+    walked = {li: _collect_label(result, i_lo * len(c.groups), i_hi * len(c.groups))
+              for li, (result, c) in enumerate(zip(results_by_label, collections))}
+    sig = None
+    if _SKELETON_CACHE:
+        sig = (dev, flags, public_call, n_obs, i_hi - i_lo, tuple(id(c) for c in collections),
+               tuple(a.tobytes() for w in walked.values() for a in w[3:]))
+        with _skeleton_lock:
+            skel = _skeletons.get(sig)
+        if skel is not None:
+            finder = _DuplicateFinder.acquire() if _DEDUP else None
+            dup, base = 0, 0
+            if finder is not None:
+                for li, w in walked.items():
+                    variant = np.zeros(len(w[1]), dtype=np.uint32) + np.uint32(li)  # any per-label constant will do here
+                    finder.representatives(base, w[1], w[2], w[3], w[4], w[5], variant)
+                    base += len(w[1])
+                dup = finder.duplicates
+                finder.release()
+            if dup == 0:
+                src = np.empty(len(skel.nbytes), dtype=np.uint64)
+                keep, at = [], 0
+                for w in walked.values():
+                    m = len(w[1])
+                    src[at: at + 2 * m: 2] = w[1]
+                    src[at + 1: at + 2 * m: 2] = w[2]
+                    at += 2 * m
+                    keep.extend(w[0])
+                arrays = HostArrays(keep, src, skel.nbytes, skel.dst)
+                local = np.ascontiguousarray(coeffs[i_lo:i_hi], dtype=np.float64)
+                t_walked = time.perf_counter()
+                with _staging_lock(dev):
+                    data = _stage_simple(skel.tables, arrays, extra=local)
+                off = _align(skel.tables.data_bytes + _lib.DATA_SLACK)
+                import dataclasses
+
+                tables = dataclasses.replace(skel.tables, coeffs=local)
+                batch = DeviceBatch.from_skeleton(skel, data, data[off: off + local.nbytes], tables, rounding)
+                batch.keepalive = keep
+                last_stage_trace = {"walk_s": t_walked - t_start, "stage_s": time.perf_counter() - t_walked, "tables_s": 0.0,
+                                    "path": "simple (cached layout)", "dedup": {"dedup_ratio": 1.0, "pubs": len(tables.pubs),
+                                                                               "distinct_pubs": len(tables.pubs),
+                                                                               "shot_bytes": None, "staged_shot_bytes": None}}
+                return batch
+    tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, collected=walked)
+    if tables.data_bytes > _SIMPLE_BYTES:
+        return None
+    t_walked = time.perf_counter()
+    with _staging_lock(dev):
+        data = _stage_simple(tables, arrays)
+    t_staged = time.perf_counter()
+    batch = DeviceBatch(tables, data, flags=flags, rounding=rounding, public_call=public_call)
+    batch.keepalive = arrays.keep
+    last_stage_trace = {"walk_s": t_walked - t_start, "stage_s": t_staged - t_walked,
+                        "tables_s": time.perf_counter() - t_staged, "path": "simple", "dedup": tables.dedup}
+    if sig is not None and tables.k1_pubs is None and batch.k2_pubs is None:
+        skel = _Skeleton(tables, arrays.nbytes, arrays.dst, batch.plan, batch.schedule, batch.labels, batch.lookup_start,
+                         batch.lookup, max(_lib.load().qcut_reduce_workspace_bytes(len(tables.coeffs), tables.n_obs), 16),
+                         tables.single_slot, list(collections))
+        with _skeleton_lock:
+            if len(_skeletons) >= 32:
+                _skeletons.pop(next(iter(_skeletons)))
+            _skeletons[sig] = skel
+    return batch
 
 
 def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo: int, i_hi: int, n_obs: int,
@@ -801,17 +937,9 @@ def stage_v2(results_by_label: list, collections: list, coeffs: np.ndarray, i_lo
     t_start = time.perf_counter()
     n_pubs = (i_hi - i_lo) * sum(len(c.groups) for c in collections)
     global last_stage_trace
-    if n_pubs <= _SIMPLE_PUBS:
-        tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, collected=collected)
-        if tables.data_bytes <= _SIMPLE_BYTES:
-            t_walked = time.perf_counter()
-            with _staging_lock(torch.cuda.current_device()):
-                data = _stage_simple(tables, arrays)
-            t_staged = time.perf_counter()
-            batch = DeviceBatch(tables, data, flags=flags, rounding=rounding, public_call=public_call)
-            batch.keepalive = arrays.keep
-            last_stage_trace = {"walk_s": t_walked - t_start, "stage_s": t_staged - t_walked,
-                                "tables_s": time.perf_counter() - t_staged, "path": "simple", "dedup": tables.dedup}
+    if n_pubs <= _SIMPLE_PUBS and collected is None:
+        batch = _stage_small(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, flags, rounding, public_call, t_start)
+        if batch is not None:
             return batch
     # The pinned ring is shared by the calls of a process on one device: concurrent callers (Python threads)
     # take turns for the staging phase -- it is PCIe bound anyway -- and run their kernels independently.

@@ -359,3 +359,46 @@ def test_small_public_calls_never_invoke_nvrtc(lib):
     batch = engine.stage_v2([results[k] for k in labels], colls, coeffs, 0, len(coeffs), len(observables["A"]), public_call=True)
     assert batch.plan.jit_state() == 0 and max(batch.plan.kernels()) <= _lib.KERNEL_SLICED_RT
     assert _hex(batch.run().cpu().numpy()) == _hex(oracle.reconstruct_exact(results, coefficients, observables))
+
+
+@pytest.mark.parametrize("rounding", ["exact", "reference"])
+def test_layout_cache_of_small_calls(lib, rounding):
+    """Repeated small calls of one layout reuse plan, schedule and uploaded tables and stage their coefficients behind the
+    shot bytes; new data, new coefficients and a changed layout must all give the oracle's result."""
+    engine._skeletons.clear()
+    want_fn = oracle.reconstruct_literal if rounding == "reference" else oracle.reconstruct_exact
+    observables = _cases.SMALL_CASES["molecular"]()[2]
+    paths = []
+    for seed in (1, 2, 3):
+        rng = np.random.default_rng(seed)
+        coefficients = _cases.random_coefficients(rng, 5)
+        results = _cases.make_results(observables, 5, 96, 3, seed=seed)  # same shapes, new bytes
+        got = reconstruct_expectation_values(results, coefficients, observables, rounding=rounding)
+        paths.append(engine.last_stage_trace["path"])
+        assert _hex(got) == _hex(want_fn(results, coefficients, observables)), seed
+    assert paths == ["simple", "simple (cached layout)", "simple (cached layout)"]
+    # another shot count -> another layout; then the first layout again -> still cached
+    results = _cases.make_results(observables, 5, 97, 3, seed=4)
+    got = reconstruct_expectation_values(results, coefficients, observables, rounding=rounding)
+    assert engine.last_stage_trace["path"] == "simple" and _hex(got) == _hex(want_fn(results, coefficients, observables))
+    results = _cases.make_results(observables, 5, 96, 3, seed=5)
+    got = reconstruct_expectation_values(results, coefficients, observables, rounding=rounding)
+    assert engine.last_stage_trace["path"] == "simple (cached layout)"
+    assert _hex(got) == _hex(want_fn(results, coefficients, observables))
+    # shared result objects (duplicates) bypass the cached layout and are still merged
+    dup = _with_duplicates(results, coefficients, [("S1", 0, 3)])
+    got = reconstruct_expectation_values(dup, coefficients, observables, rounding=rounding)
+    assert engine.last_stage_trace["path"] == "simple" and engine.last_stage_trace["dedup"]["dedup_ratio"] > 1.0
+    assert _hex(got) == _hex(want_fn(dup, coefficients, observables))
+
+
+def test_mid_size_calls_pipeline_gather_and_copy(lib):
+    """4..64 MiB: the simple path hands the gather + copy to qcut_stage_h2d (2 MiB pieces, four threads)."""
+    rng = np.random.default_rng(31)
+    observables = {"A": _cases.random_paulis(rng, 6, 40, 1, 5, "Z")}
+    coefficients = _cases.random_coefficients(rng, 3)
+    results = _cases.make_results(observables, 3, 400_000, 2, seed=32)  # 3 x 400 000 x (5 + 1) bytes = 7.2 MB
+    for _ in range(2):  # second call: cached layout, same pipeline
+        got = reconstruct_expectation_values(results, coefficients, observables)
+        assert _hex(got) == _hex(oracle.reconstruct_exact(results, coefficients, observables))
+    assert engine.last_stage_trace["path"] == "simple (cached layout)"

@@ -794,14 +794,14 @@ _PIPELINE_FROM = 4 << 20      # simple path: from this size on the gather and th
 def _stage_simple(tables: HostTables, arrays: HostArrays, extra: np.ndarray | None = None) -> torch.Tensor:
     """Small inputs: gather every borrowed buffer into the pinned buffer, ONE host-to-device copy on the current
     stream (no threads, nothing pipelined: for tutorial-sized calls the pipeline's fixed costs were the larger part
-    of the call).  From 4 MiB on, ``qcut_stage_h2d`` gathers 2 MiB pieces on four threads and copies each as soon as
-    it is complete.  ``extra`` (the coefficients of a cached layout) travels behind the shot bytes, at
+    of the call).  From 4 MiB on, ``qcut_stage_h2d`` gathers 2 MiB pieces on eight threads and copies each as soon as
+    it is complete (cfg2, 30 MB: 1.0 ms with four threads).  ``extra`` (the coefficients of a cached layout) travels behind the shot bytes, at
     ``_align(data_bytes + DATA_SLACK)``, in the same copy."""
     dev = torch.cuda.current_device()
     n = tables.data_bytes
     extra_off = _align(n + _lib.DATA_SLACK)
     total = extra_off + (extra.nbytes if extra is not None else 0)
-    pinned = _pinned_buffer(max(total, 8 << 20))
+    pinned = _pinned_buffer(max(total, 16 << 20))
     done = _copy_done.get(dev)
     if done is not None:
         done.synchronize()  # a previous call's copy may still be reading the pinned buffer
@@ -809,7 +809,7 @@ def _stage_simple(tables: HostTables, arrays: HostArrays, extra: np.ndarray | No
     if n >= _PIPELINE_FROM and len(arrays):
         check(
             _lib.load().qcut_stage_h2d(_lib.np_ptr(arrays.src), _lib.np_ptr(arrays.nbytes), _lib.np_ptr(arrays.dst), len(arrays),
-                                       pinned.data_ptr(), 8 << 20, data.data_ptr(), 4, _stream_ptr()),
+                                       pinned.data_ptr(), 16 << 20, data.data_ptr(), 8, _stream_ptr()),
             "qcut_stage_h2d",
         )  # returns when the bytes have left the pinned pieces
         if extra is not None:

@@ -23,7 +23,9 @@ KEYS = [
     "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
     "lts__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
-    "smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.pct", "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_requests_srcunit_tex_op_read.sum",
+    "memory_l2_theoretical_sectors_global", "memory_l2_theoretical_sectors_global_ideal", "dram__sectors_read.sum",
 ]
 for r in rows[2:]:
     print("=== kernel", r[hdr.index("Kernel Name")], "launch id", r[0])
@@ -36,5 +38,19 @@ for r in rows[2:]:
                 vals[h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")] = float(r[i])
             except ValueError:
                 pass
+    def num(name):
+        try:
+            return float(r[hdr.index(name)].replace(",", ""))
+        except (ValueError, IndexError):
+            return float("nan")
+
+    # L2 / sector efficiency of the shot-byte stream (north star): sectors per global-load request (a fully used warp-wide
+    # 128-bit load is 16 sectors of 32 B), bytes the L2 delivered to the SMs per byte read from DRAM, and the
+    # requested-vs-ideal sector ratio ncu derives for global loads (1.0 = no partially used sectors)
+    sec, req = num("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"), num("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum")
+    l2s, drs = num("lts__t_sectors_srcunit_tex_op_read.sum"), num("dram__sectors_read.sum")
+    the, ideal = num("memory_l2_theoretical_sectors_global"), num("memory_l2_theoretical_sectors_global_ideal")
+    print(f"  derived: global-load sectors per request {sec / req if req else float('nan'):.2f}; L2->SM read sectors / DRAM read sectors "
+          f"{l2s / drs if drs else float('nan'):.3f}; requested / ideal L2 sectors of global accesses {the / ideal if ideal else float('nan'):.3f}")
     top = sorted(vals.items(), key=lambda kv: -kv[1])[:8]
     print("  stalls (warps per issue-active cycle):", ", ".join(f"{k} {v:.2f}" for k, v in top))

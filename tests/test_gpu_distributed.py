@@ -83,12 +83,15 @@ print("rank", rank, "ok")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_nccl_reconstruction(tmp_path):
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_two_rank_nccl_reconstruction(tmp_path, nproc):
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, QCUT_ROOT=str(ROOT))
     proc = subprocess.run(
-        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
          "--master-port", "29631", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
-    assert proc.stdout.count("ok") >= 2
+    assert proc.stdout.count("ok") >= nproc

@@ -139,3 +139,65 @@ def test_expectation_values_at_a_million_shots_vs_literal_oracle(lib, shots, exa
     print(f"\nS={shots}: max|ours-literal|={np.max(np.abs(ours - literal_vals)):.3e} max|ours-exact|="
           f"{np.max(np.abs(ours - exact_vals)):.3e} max|literal-exact|={np.max(np.abs(literal_vals - exact_vals)):.3e} "
           f"max|E|={np.max(np.abs(exact_vals)):.3e} reference-rounding mode: bit-identical")
+
+
+def _host_reduce_inputs(tables, values):
+    """term[i, k] = c_i * prod_label E[label, i, k] from a per-(PUB, term) value table, vectorised (single-slot lookups),
+    multiplied in the reference's order: ones * E_label0 * E_label1 * ... then * coeff (cutting_reconstruction.py:135,163-168)."""
+    C, K = len(tables.coeffs), tables.n_obs
+    cur = np.ones((C, K))
+    i = np.arange(C, dtype=np.int64)[:, None]
+    for lab in tables.labels:
+        base, G, lb = int(lab["pub_base"]), int(lab["num_groups"]), int(lab["lookup_base"])
+        slots = tables.lookup[tables.lookup_start[lb: lb + K]]
+        pub = base + i * G + slots["group"].astype(np.int64)[None, :]
+        idx = tables.pubs["tally_offset"].astype(np.int64)[pub] + slots["term"].astype(np.int64)[None, :]
+        cur = cur * values[idx]
+    return tables.coeffs[:, None] * cur
+
+
+@pytest.mark.parametrize("name", ["cfg4_heavy_hex", "cfg5_molecular"])
+def test_full_size_shapes_against_the_oracle(lib, name):
+    """BASELINE-sized cfg4 / cfg5 (scale 1.0, biased data).  Tallies: the specialised kernels against the run-time-mask
+    kernels on every PUB and against the C oracle on a sample.  Expectation values: the default mode against a NumPy
+    reduction of the exact tallies; the reference-rounding mode BIT-IDENTICAL to the strictly sequential NumPy sum
+    (cumsum) of its own per-PUB values, which in turn are bit-identical to the C restatement of the reference's
+    shot-by-shot accumulation on the sample."""
+    w = W.get_workload(name, 1.0)
+    tables = W.build_tables(w)
+    assert tables.single_slot
+    data = W.device_data(tables, seed=w.seed)
+    batch, tallies, out = _run(tables, data, 0)
+    _, t_rt, out_rt = _run(tables, data, _lib.PLAN_NO_JIT)
+    assert torch.equal(tallies, t_rt) and torch.equal(out, out_rt)
+    t_host = tallies.cpu().numpy()
+    shots = tables.pubs["shots"].astype(np.float64)
+    T_of = tables.groups["n_terms"][tables.pubs["group"]].astype(np.int64)
+    exact_e = t_host / np.repeat(shots, T_of)
+    terms = _host_reduce_inputs(tables, exact_e)
+    kappa = float(np.abs(tables.coeffs).sum())
+    ours = out.cpu().numpy()
+    assert np.max(np.abs(ours - terms.sum(axis=0))) <= 1e-11 * max(kappa, 1.0)
+    # reference rounding at full size
+    lit = engine.DeviceBatch(tables, data, rounding="reference")
+    lit_out = lit.run().cpu().numpy()
+    e_lit = lit.expvals[: tables.n_tallies].cpu().numpy()
+    seq = np.cumsum(_host_reduce_inputs(tables, e_lit), axis=0)[-1]  # strictly sequential, like expvals += ... (:168)
+    assert [v.hex() for v in lit_out] == [v.hex() for v in seq]
+    # sample of PUBs against the C oracle: int64 tallies and the reference's shot-by-shot fp64 values
+    rng = np.random.default_rng(w.seed + 1)
+    worst = 0.0
+    for p in rng.choice(len(tables.pubs), size=24, replace=False):
+        pub = tables.pubs[p]
+        grp = tables.groups[pub["group"]]
+        nb, T, S, nbq = int(grp["nb_obs"]), int(grp["n_terms"]), int(pub["shots"]), int(pub["nb_qpd"])
+        obs = data[int(pub["obs_offset"]): int(pub["obs_offset"]) + S * nb].cpu().numpy().reshape(S, nb)
+        qpd = data[int(pub["qpd_offset"]): int(pub["qpd_offset"]) + S * nbq].cpu().numpy().reshape(S, nbq)
+        masks = tables.masks[int(grp["mask_offset"]): int(grp["mask_offset"]) + T * nb].reshape(T, nb)
+        e_seq, want = c_oracle.pub(obs, qpd, masks)
+        sl = slice(int(pub["tally_offset"]), int(pub["tally_offset"]) + T)
+        assert np.array_equal(t_host[sl], want), (name, int(p))
+        assert [v.hex() for v in e_lit[sl]] == [v.hex() for v in e_seq], (name, int(p))
+        worst = max(worst, float(np.max(np.abs(e_seq - want / S))))
+    print(f"\n{name} at scale 1.0: max|default - numpy reduction| = {np.max(np.abs(ours - terms.sum(axis=0))):.3e} (kappa {kappa:.0f}); "
+          f"max|reference mode - default| = {np.max(np.abs(lit_out - ours)):.3e}; reference's per-PUB noise on the sample {worst:.3e}")

@@ -91,3 +91,17 @@ def test_product_never_imports_the_oracle():
     for path in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*")):
         if path.suffix in (".py", ".cu", ".cuh", ".h"):
             assert not re.search(r"^\s*(from|import)\s+oracle|oracle_seq", path.read_text(), re.M), path
+
+
+def test_no_coefficients_returns_zeros_like_the_reference():
+    """coefficients=[] with empty results: the reference's loops do not execute and it returns zeros
+    (cutting_reconstruction.py:112,133-170); no device is needed for that."""
+    from oracle import oracle
+    from qiskit_addon_cutting_b200 import PauliList, PrimitiveResult, reconstruct_expectation_values
+
+    observables = {"A": PauliList(["ZI", "IZ", "XX"]), "B": PauliList(["ZZ", "XI", "IX"])}
+    results = {"A": PrimitiveResult([]), "B": PrimitiveResult([])}
+    got = reconstruct_expectation_values(results, [], observables)
+    assert got == [0.0, 0.0, 0.0] and all(isinstance(v, np.float64) for v in got)
+    assert got == oracle.reconstruct_literal(results, [], observables)
+    assert reconstruct_expectation_values(PrimitiveResult([]), [], PauliList(["ZZ", "XX"])) == [0.0, 0.0]

@@ -192,6 +192,12 @@ int qcut_quasi_launch(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_gr
                       const uint64_t* d_mask_limbs, const int64_t* d_dist_start,
                       const uint64_t* d_obs_bits, int n_limbs_obs, const uint64_t* d_qpd_bits,
                       int n_limbs_qpd, const double* d_weights, double* d_expvals, void* stream);
+/* int64 tallies -> fp64 expectation values of the PUBs of a (device) PUB table: d_expvals[pub.tally_offset + t] =
+ * d_tallies[...] / pub.shots (correctly rounded; 0 for PUBs without shots), t < n_terms of the PUB's group in `plan`.
+ * For calls that mix SamplerV1 and SamplerV2 subsystems (the reference decides per subsystem,
+ * cutting_reconstruction.py:143,150): both kinds then feed one qcut_reduce_expvals_launch. */
+int qcut_tallies_to_expvals_launch(const qcut_plan* plan, const qcut_pub_desc* d_pubs, int64_t n_pubs,
+                                   const int64_t* d_tallies, double* d_expvals, void* stream);
 /* K2 on fp64 per-PUB expectation values instead of tallies (V1 path). */
 int qcut_reduce_expvals_launch(const double* d_expvals, const qcut_pub_desc* d_pubs,
                                const qcut_label_desc* d_labels, int n_labels,

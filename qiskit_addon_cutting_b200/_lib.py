@@ -98,6 +98,7 @@ SIGNATURES = {
     "qcut_reduce_workspace_bytes": (_SZ, [_I64, _INT]),
     "qcut_reduce_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
     "qcut_expvals_literal_launch": (_INT, [_VP, _VP, _VP, _VP, _I64, _VP]),
+    "qcut_tallies_to_expvals_launch": (_INT, [_VP, _VP, _I64, _VP, _VP, _VP]),
     "qcut_quasi_launch": (_INT, [_VP, _I64, _VP, _VP, _VP, _VP, _INT, _VP, _INT, _VP, _VP, _VP]),
     "qcut_reduce_expvals_launch": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP, _VP, _I64, _INT, _VP, _VP, _INT, _VP]),
     "qcut_recombine_launch": (_INT, [_VP, _INT, _VP, _VP, _VP, _INT, _VP, _VP]),

@@ -53,6 +53,7 @@ int launch_reduce(const TallyT*, const qcut_pub_desc*, const qcut_label_desc*, i
                   const qcut_slot*, const double*, int64_t, int, double*, void*, bool, bool, cudaStream_t);
 size_t reduce_workspace_bytes(int64_t, int);
 int launch_literal(const qcut_plan*, const uint8_t*, const qcut_pub_desc*, int64_t, double*, cudaStream_t);
+int launch_tallies_to_expvals(const qcut_plan*, const qcut_pub_desc*, int64_t, const int64_t*, double*, cudaStream_t);
 int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const uint64_t*, const int64_t*,
                  const uint64_t*, int, const uint64_t*, int, const double*, double*, cudaStream_t);
 int launch_recombine(const double*, bool, const uint32_t*, const uint32_t*, const double*, int, double*, cudaStream_t);
@@ -547,6 +548,13 @@ int qcut_expvals_literal_launch(const qcut_plan* plan, const qcut_schedule* sche
   // PUBs without shots write nothing: their expectation values stay 0 like the reference's (its loop does not run)
   if (n_expvals > 0) QCUT_CUDA(cudaMemsetAsync(d_expvals, 0, sizeof(double) * (size_t)n_expvals, s));
   return launch_literal(plan, d_data, schedule->d_pubs, schedule->n_pubs, d_expvals, s);
+}
+
+int qcut_tallies_to_expvals_launch(const qcut_plan* plan, const qcut_pub_desc* d_pubs, int64_t n_pubs,
+                                   const int64_t* d_tallies, double* d_expvals, void* stream) {
+  if (!plan || n_pubs < 0 || (n_pubs > 0 && (!d_pubs || !d_tallies || !d_expvals)))
+    return set_error("qcut_tallies_to_expvals_launch: bad argument"), QCUT_ERR_INVALID;
+  return launch_tallies_to_expvals(plan, d_pubs, n_pubs, d_tallies, d_expvals, static_cast<cudaStream_t>(stream));
 }
 
 int qcut_quasi_launch(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_group_desc* d_groups,

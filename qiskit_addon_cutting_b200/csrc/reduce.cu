@@ -459,6 +459,29 @@ int launch_quasi(const qcut_pub_desc* d_pubs, int64_t n_pubs, const qcut_group_d
   return QCUT_OK;
 }
 
+// ---- int64 tallies -> fp64 expectation values, E = tally / shots (one correctly rounded division, 0 for PUBs without
+// shots): what K2 does on the fly, as a table for calls that mix SamplerV1 and SamplerV2 subsystems ----
+__global__ void __launch_bounds__(128)
+tallies_to_expvals_kernel(const qcut_pub_desc* __restrict__ pubs, int64_t n_pubs, const GroupDev* __restrict__ groups,
+                          const int64_t* __restrict__ tallies, double* __restrict__ expvals) {
+  for (int64_t p = blockIdx.x; p < n_pubs; p += gridDim.x) {
+    const qcut_pub_desc pub = pubs[p];
+    const uint32_t T = groups[pub.group].n_terms;
+    for (uint32_t t = threadIdx.x; t < T; t += blockDim.x)
+      expvals[pub.tally_offset + t] = pub.shots ? __ddiv_rn((double)tallies[pub.tally_offset + t], (double)pub.shots) : 0.0;
+  }
+}
+
+int launch_tallies_to_expvals(const qcut_plan* plan, const qcut_pub_desc* d_pubs, int64_t n_pubs, const int64_t* d_tallies,
+                              double* d_expvals, cudaStream_t stream) {
+  if (n_pubs <= 0) return QCUT_OK;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  tallies_to_expvals_kernel<<<(unsigned)(n_pubs < cap ? n_pubs : cap), 128, 0, stream>>>(d_pubs, n_pubs, plan->d_groups,
+                                                                                          d_tallies, d_expvals);
+  QCUT_CUDA(cudaGetLastError());
+  return QCUT_OK;
+}
+
 // ---- term recombination: out[r] = sum_j coeff[j] * e[index[j]] (complex fp64, reference order) ----
 // One warp per observable: the lanes form 128 products at a time (coalesced coefficient loads, gathered
 // expectation values, four independent loads in flight per lane) and park them in shared memory; lane 0

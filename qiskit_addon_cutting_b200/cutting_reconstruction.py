@@ -157,10 +157,6 @@ def reconstruct_expectation_values(
     coeffs = np.array([float(c[0]) for c in coefficients], dtype=np.float64)
     labels = list(collections)
     v1 = [_is_sampler_v1(results_dict[label]) for label in labels]
-    if any(v1) and not all(v1):
-        raise ValueError(
-            "Mixing SamplerV1 and SamplerV2 results across subsystems is not supported by the B200 path."
-        )
 
     # Everything below needs the CUDA library and a device; no CPU fallback exists.
     import torch
@@ -178,8 +174,9 @@ def reconstruct_expectation_values(
     if world == 1:
         if len(coeffs) == 0 or not labels:
             return list(np.zeros(n_obs))  # the reference's loops do not execute: expvals stay 0 (:133-170)
-        if all(v1):
-            out = quasi.reconstruct_v1(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, sequential=literal)
+        if any(v1):  # SamplerV1 subsystems, possibly mixed with SamplerV2 ones (the reference decides per subsystem, :143)
+            out = quasi.reconstruct_v1(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, sequential=literal,
+                                       v1=v1, rounding=rounding)
         else:
             out = engine.stage_v2(result_list, collection_list, coeffs, 0, len(coeffs), n_obs, rounding=rounding,
                                   public_call=True).run()
@@ -224,9 +221,9 @@ def reconstruct_expectation_values(
         if error is None:
             try:
                 if sharding.i_hi > sharding.i_lo and labels:
-                    if all(v1):
+                    if any(v1):
                         part = quasi.reconstruct_v1(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs,
-                                                    sequential=literal)
+                                                    sequential=literal, v1=v1, rounding=rounding)
                     else:
                         part = engine.stage_v2(result_list, collection_list, coeffs, sharding.i_lo, sharding.i_hi, n_obs,
                                                collected=sharding.collected or None, rounding=rounding,

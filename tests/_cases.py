@@ -255,3 +255,35 @@ TERMS_CASES = {
     "complex": lambda: terms_case(1202, True),
     "single_qubit": lambda: terms_case(1203, False, n_qubits=1, pool=8, n_observables=6),
 }
+
+
+# ---- SamplerV1 views of SamplerV2 results (for inputs that mix the two, reference cutting_reconstruction.py:143,150) ----
+def to_sampler_v1(result, observables):
+    """``SamplerResult`` whose quasi-distributions are the outcome frequencies of a ``PrimitiveResult``'s PUBs: the
+    outcome integer is ``(qpd << num_measured_bits) | obs`` (reference ``_process_outcome``, :173-193)."""
+    from qiskit_addon_cutting_b200.containers import QuasiDistribution, SamplerResult
+
+    groups = ObservableCollection(observables).groups
+    dists = []
+    for idx in range(len(result)):
+        data = result[idx].data
+        nmb = groups[idx % len(groups)].num_measured_bits
+        obs, qpd = data.observable_measurements.array, data.qpd_measurements.array
+        counts: dict = {}
+        for j in range(qpd.shape[0]):
+            o = int.from_bytes(obs[j].tobytes(), "big") & ((1 << nmb) - 1)
+            key = (int.from_bytes(qpd[j].tobytes(), "big") << nmb) | o
+            counts[key] = counts.get(key, 0) + 1
+        shots = max(qpd.shape[0], 1)
+        dists.append(QuasiDistribution({k: v / shots for k, v in counts.items()}))
+    return SamplerResult(dists)
+
+
+def case_mixed_samplers(seed=1010, shots=60):
+    """Three subsystems: SamplerV2, SamplerV1, SamplerV2 -- the reference handles each subsystem by its own type."""
+    rng = np.random.default_rng(seed)
+    observables = {"A": random_paulis(rng, 8, 7, 0, 4), "B": random_paulis(rng, 8, 5, 0, 4), "C": random_paulis(rng, 8, 9, 1, 5, "Z")}
+    coeffs = random_coefficients(rng, 5)
+    results = make_results(observables, 5, lambda label, i, g: shots + i, 2, seed + 1)
+    results["B"] = to_sampler_v1(results["B"], observables["B"])
+    return results, coeffs, observables

@@ -402,3 +402,21 @@ def test_mid_size_calls_pipeline_gather_and_copy(lib):
         got = reconstruct_expectation_values(results, coefficients, observables)
         assert _hex(got) == _hex(oracle.reconstruct_exact(results, coefficients, observables))
     assert engine.last_stage_trace["path"] == "simple (cached layout)"
+
+
+@pytest.mark.parametrize("rounding", ["exact", "reference"])
+def test_mixed_sampler_v1_and_v2_subsystems(lib, rounding):
+    """The reference decides V1 / V2 per subsystem (cutting_reconstruction.py:143,150): SamplerV2 subsystems go through
+    ingest + K1, SamplerV1 ones through the quasi kernel, one K2 launch consumes both in the caller's subsystem order."""
+    results, coefficients, observables = _cases.case_mixed_samplers()
+    want = oracle.reconstruct_literal if rounding == "reference" else oracle.reconstruct_exact
+    got = reconstruct_expectation_values(results, coefficients, observables, rounding=rounding)
+    assert _hex(got) == _hex(want(results, coefficients, observables))
+    # the other way round, and with shared (duplicate) SamplerV2 PUBs
+    flipped = {k: results[k] for k in ("B", "C", "A")}
+    obs_flipped = {k: observables[k] for k in ("B", "C", "A")}
+    got = reconstruct_expectation_values(flipped, coefficients, obs_flipped, rounding=rounding)
+    assert _hex(got) == _hex(want(flipped, coefficients, obs_flipped))
+    dup = _with_duplicates(results, coefficients, [("A", 0, 2), ("C", 1, 4)])
+    got = reconstruct_expectation_values(dup, coefficients, observables, rounding=rounding)
+    assert _hex(got) == _hex(want(dup, coefficients, observables))

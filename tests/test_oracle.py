@@ -129,3 +129,18 @@ def test_empty_and_edge_pubs():
     o = np.array([[1]], np.uint8)
     assert oracle.tally_exact(o, np.array([[0x80]], np.uint8), [1])[0] == 1
     assert oracle.tally_exact(o, np.array([[0x00]], np.uint8), [1])[0] == -1
+
+
+def test_oracle_matches_the_reference_text_on_mixed_sampler_inputs():
+    """SamplerV1 and SamplerV2 subsystems in one call (the reference decides per subsystem, :143,150): the literal oracle
+    reproduces what the reference's own text returns, bit for bit."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference sources not available")
+    import _cases
+
+    results, coefficients, observables = _cases.case_mixed_samplers()
+    ref = ref_loader.load_reference()["reconstruct_expectation_values"](results, coefficients, observables)
+    got = oracle.reconstruct_literal(results, coefficients, observables)
+    assert [float(v).hex() for v in got] == [float(v).hex() for v in ref]

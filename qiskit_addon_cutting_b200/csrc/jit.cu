@@ -174,7 +174,8 @@ static bool emit_terms(std::ostringstream& os, const std::string& name, const qc
 // compile time stays linear in the number of groups) and the kernel dispatches on the group's
 // variant index; the schedule lists a kernel's tiles variant by variant, so at any moment the SMs
 // execute a handful of functions.
-std::string generate_multi_source(const std::vector<const qcut_group_desc*>& gds, const uint8_t* masks, int threads) {
+std::string generate_multi_source(const std::vector<const qcut_group_desc*>& gds, const uint8_t* masks, int threads,
+                                  int min_blocks) {
   std::ostringstream os;
   os << kPrelude << "\n";
   for (size_t v = 0; v < gds.size(); ++v) {
@@ -187,7 +188,7 @@ std::string generate_multi_source(const std::vector<const qcut_group_desc*>& gds
           "  qcut_flush<Terms" << v << "::T>(acc, ns, lane, tally);\n"
           "}\n\n";
   }
-  os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 2)\n"
+  os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n"
         "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
         "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
         "                  unsigned long long* __restrict__ tallies, const QcutGroup* __restrict__ groups) {\n"
@@ -223,6 +224,11 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   const int budget = ((nb > 4 && !split) ? 64 : 32) + (int)((T + 3) / 4) + 28;
   int min_blocks = budget > 128 ? 1 : 2;
   if (split && threads * 3 * (budget + 8) <= 65536) min_blocks = 3;  // one block at a time: three CTAs share an SM
+  if (!split && nb <= 8) {
+    // narrow rows with few terms are memory-latency bound: more CTAs per SM when the registers allow it
+    const char* env_auto = std::getenv("QCUT_JIT_AUTO_MINBLOCKS");
+    if (!(env_auto && *env_auto && std::atoi(env_auto) == 0)) min_blocks = budget <= 64 ? 4 : budget <= 84 ? 3 : min_blocks;
+  }
   if (min_blocks_out && *min_blocks_out > 0) min_blocks = *min_blocks_out;  // explicit override
   if (min_blocks_out) *min_blocks_out = min_blocks;
 
@@ -554,9 +560,17 @@ int jit_build(qcut_plan* plan, bool load) {
       std::vector<const qcut_group_desc*> gds;
       for (int g : jk.variants) gds.push_back(&plan->groups[g]);
       jk.threads = 256;
-      jk.min_blocks = 2;
+      // Groups of a few terms on narrow rows need few registers (32 planes per 32-bit block + packed counters + ~28):
+      // these kernels wait on memory (ncu: long_scoreboard 4.5 warps per issue at 16 warps per SM), so they get as
+      // many CTAs per SM as their widest variant allows.  QCUT_JIT_MULTI_MINBLOCKS overrides.
+      int budget = 0;
+      for (const qcut_group_desc* gd : gds)
+        budget = std::max(budget, (gd->nb_obs > 4 ? 64 : 32) + (int)((gd->n_terms + 3) / 4) + 28);
+      jk.min_blocks = budget <= 64 ? 4 : budget <= 84 ? 3 : 2;
+      if (const char* env_mb = std::getenv("QCUT_JIT_MULTI_MINBLOCKS"))
+        if (*env_mb && std::atoi(env_mb) >= 1 && std::atoi(env_mb) <= 8) jk.min_blocks = std::atoi(env_mb);
       jk.staged = false;
-      jk.source = generate_multi_source(gds, plan->masks.data(), jk.threads);
+      jk.source = generate_multi_source(gds, plan->masks.data(), jk.threads, jk.min_blocks);
       rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
       return;
     }

@@ -845,6 +845,7 @@ class _Skeleton:
     workspace_bytes: int
     single_slot: bool
     collections: list  # keeps the ids in the signature unique
+    dedup: dict = field(default_factory=dict)  # tables.dedup of the layout (no duplicates by construction)
 
 
 _skeletons: dict = {}
@@ -897,9 +898,7 @@ def _stage_small(results_by_label: list, collections: list, coeffs: np.ndarray, 
                 batch = DeviceBatch.from_skeleton(skel, data, data[off: off + local.nbytes], tables, rounding)
                 batch.keepalive = keep
                 last_stage_trace = {"walk_s": t_walked - t_start, "stage_s": time.perf_counter() - t_walked, "tables_s": 0.0,
-                                    "path": "simple (cached layout)", "dedup": {"dedup_ratio": 1.0, "pubs": len(tables.pubs),
-                                                                               "distinct_pubs": len(tables.pubs),
-                                                                               "shot_bytes": None, "staged_shot_bytes": None}}
+                                    "path": "simple (cached layout)", "dedup": skel.dedup}
                 return batch
     tables, arrays = build_host_tables(results_by_label, collections, coeffs, i_lo, i_hi, n_obs, collected=walked)
     if tables.data_bytes > _SIMPLE_BYTES:
@@ -915,7 +914,7 @@ def _stage_small(results_by_label: list, collections: list, coeffs: np.ndarray, 
     if sig is not None and tables.k1_pubs is None and batch.k2_pubs is None:
         skel = _Skeleton(tables, arrays.nbytes, arrays.dst, batch.plan, batch.schedule, batch.labels, batch.lookup_start,
                          batch.lookup, max(_lib.load().qcut_reduce_workspace_bytes(len(tables.coeffs), tables.n_obs), 16),
-                         tables.single_slot, list(collections))
+                         tables.single_slot, list(collections), tables.dedup)
         with _skeleton_lock:
             if len(_skeletons) >= 32:
                 _skeletons.pop(next(iter(_skeletons)))

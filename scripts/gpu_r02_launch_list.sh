@@ -28,7 +28,7 @@ with open("gpurun_out/r02_cfg4_bench_launches_summary.txt", "w") as f:
         print(line)
     k1 = t.get("qcut_tally_sliced", 0.0)
     k2 = sum(v for k, v in t.items() if k.startswith("void qcut::reduce") or k.startswith("reduce"))
-    step = [v for k, v in t.items() if "literal" not in k]
+    step = [v for k, v in t.items() if "literal" not in k and "reduce_partial_kernel<double" not in k]
     f.write(f"K1 share of the default-mode kernels (qcut_tally_sliced / (all but the literal pass)): {k1 / sum(step):.3f}\n")
     print(f"K1 share {k1 / sum(step):.3f}")
 PY

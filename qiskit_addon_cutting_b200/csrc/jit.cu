@@ -225,9 +225,9 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   int min_blocks = budget > 128 ? 1 : 2;
   if (split && threads * 3 * (budget + 8) <= 65536) min_blocks = 3;  // one block at a time: three CTAs share an SM
   if (!split && nb <= 8) {
-    // narrow rows with few terms are memory-latency bound: more CTAs per SM when the registers allow it
+    // experiment knob (measured slower, see the multi-group kernels in jit_build): more CTAs per SM for small budgets
     const char* env_auto = std::getenv("QCUT_JIT_AUTO_MINBLOCKS");
-    if (!(env_auto && *env_auto && std::atoi(env_auto) == 0)) min_blocks = budget <= 64 ? 4 : budget <= 84 ? 3 : min_blocks;
+    if (env_auto && *env_auto && std::atoi(env_auto) != 0) min_blocks = budget <= 64 ? 4 : budget <= 84 ? 3 : min_blocks;
   }
   if (min_blocks_out && *min_blocks_out > 0) min_blocks = *min_blocks_out;  // explicit override
   if (min_blocks_out) *min_blocks_out = min_blocks;
@@ -560,13 +560,11 @@ int jit_build(qcut_plan* plan, bool load) {
       std::vector<const qcut_group_desc*> gds;
       for (int g : jk.variants) gds.push_back(&plan->groups[g]);
       jk.threads = 256;
-      // Groups of a few terms on narrow rows need few registers (32 planes per 32-bit block + packed counters + ~28):
-      // these kernels wait on memory (ncu: long_scoreboard 4.5 warps per issue at 16 warps per SM), so they get as
-      // many CTAs per SM as their widest variant allows.  QCUT_JIT_MULTI_MINBLOCKS overrides.
-      int budget = 0;
-      for (const qcut_group_desc* gd : gds)
-        budget = std::max(budget, (gd->nb_obs > 4 ? 64 : 32) + (int)((gd->n_terms + 3) / 4) + 28);
-      jk.min_blocks = budget <= 64 ? 4 : budget <= 84 ? 3 : 2;
+      // Two CTAs per SM (128 registers).  These kernels wait on memory (ncu: long_scoreboard 4.5 warps per issue at 16
+      // warps per SM) and their groups need only ~60 registers on paper, but more CTAs per SM measured SLOWER on B200
+      // (cfg5: 0.73 of HBM at 2 CTAs/SM, 0.59 at 3, 0.56 at 4; cfg3 local 0.746 / 0.737 / 0.728): under a lower cap
+      // ptxas spills the row registers it keeps in flight.  QCUT_JIT_MULTI_MINBLOCKS overrides (experiments).
+      jk.min_blocks = 2;
       if (const char* env_mb = std::getenv("QCUT_JIT_MULTI_MINBLOCKS"))
         if (*env_mb && std::atoi(env_mb) >= 1 && std::atoi(env_mb) <= 8) jk.min_blocks = std::atoi(env_mb);
       jk.staged = false;

@@ -70,10 +70,10 @@ struct TermEmitter {
     for (uint32_t b = b0; b < b1; ++b) d += __builtin_popcount((unsigned)(row(s)[b] ^ row(t)[b]));
     return d;
   }
-  void count(uint32_t t, const char* word) {
+  void count(uint32_t t, const char* word, bool popc = true) {
     // term t lives in field t / NACC of packed register t % NACC: consecutive terms touch different
     // registers, so their popcount -> add chains are independent
-    os << "    acc[" << t % nacc << "] += (uint32_t)__popc(" << word << ")";
+    os << "    acc[" << t % nacc << "] += " << (popc ? "(uint32_t)__popc(" : "(") << word << ")";
     if (t / nacc) os << " << " << 8 * (t / nacc);
     os << ";\n";
   }
@@ -117,7 +117,8 @@ struct TermEmitter {
 }  // namespace
 
 // Returns true when the split form (run0 / run1) was emitted.
-static bool emit_terms(std::ostringstream& os, const std::string& name, const qcut_group_desc& gd, const uint8_t* masks) {
+static bool emit_terms(std::ostringstream& os, const std::string& name, const qcut_group_desc& gd, const uint8_t* masks,
+                       bool* pipe_out = nullptr, bool* sacc_out = nullptr, bool* il_out = nullptr) {
   const uint32_t T = gd.n_terms, nb = gd.nb_obs, nacc = (T + 3) / 4;
   TermEmitter em{os, gd, masks, T, nb, nacc};
   std::vector<uint32_t> all(T);
@@ -166,6 +167,139 @@ static bool emit_terms(std::ostringstream& os, const std::string& name, const qc
              [&](uint32_t t, const char* w) { em.count(t, w); }, p1);
     os << "  }\n";
   }
+  // 8-byte rows, loads of the next step inside the network (qcut_warp_pipe): terms ordered so that bit-planes are
+  // finished as early as possible -- repeatedly take the live plane with the fewest unevaluated terms and evaluate
+  // those (min-degree elimination) -- and one 16-byte load of the next step after every four planes that died.
+  // Every term is built from scratch (no chaining), so this form is only offered for sparse masks (what a local
+  // observable restricted to a subsystem looks like); `pipe_out` says whether it was emitted.
+  bool pipe = false;
+  if (nb == 8 && pipe_out) {
+    size_t lop3 = 0;
+    for (uint32_t t = 0; t < T; ++t) lop3 += (size_t)(em.weight(t, 0, 8) + 1) / 2;
+    std::vector<std::vector<uint32_t>> of_plane(64);
+    std::vector<int> open_terms(64, 0);
+    for (uint32_t t = 0; t < T; ++t)
+      for (uint32_t p = 0; p < 64; ++p)
+        if ((em.row(t)[p >> 3] >> (p & 7)) & 1u) { of_plane[p].push_back(t); ++open_terms[p]; }
+    std::vector<uint32_t> order;
+    std::vector<int> dead_after;  // planes finished once order[i] has been evaluated
+    std::vector<bool> done(T, false);
+    int dead = 0;
+    for (uint32_t p = 0; p < 64; ++p) dead += open_terms[p] == 0;
+    auto evaluate = [&](uint32_t t) {
+      done[t] = true;
+      for (uint32_t p = 0; p < 64; ++p)
+        if ((em.row(t)[p >> 3] >> (p & 7)) & 1u) dead += --open_terms[p] == 0;
+      order.push_back(t);
+      dead_after.push_back(dead);
+    };
+    for (uint32_t t = 0; t < T; ++t)
+      if (em.weight(t, 0, 8) == 0) evaluate(t);
+    while (order.size() < T) {
+      int best = -1;
+      for (int p = 0; p < 64; ++p)
+        if (open_terms[p] > 0 && (best < 0 || open_terms[p] < open_terms[best])) best = p;
+      for (uint32_t t : of_plane[(size_t)best])
+        if (!done[t]) evaluate(t);
+    }
+    // worth it when the masks are sparse and half of the planes are finished after three quarters of the terms
+    pipe = lop3 <= (size_t)T * 2 && dead_after[(size_t)(3 * T / 4 > 0 ? 3 * T / 4 - 1 : 0)] >= 32;
+    if (pipe) {
+      os << "  static QCUT_MDEV void run_pf(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, const uint32_t qp,\n"
+            "                               uint32_t* __restrict__ acc, const uint8_t* __restrict__ nsrc, const uint32_t pfv,\n"
+            "                               uint32_t* __restrict__ NA) {\n    (void)Q;\n    uint32_t x, c = 0;\n";
+      int issued = 0;
+      {  // planes no term reads are free from the start
+        int dead0 = 0;
+        for (uint32_t p = 0; p < 64; ++p) dead0 += of_plane[p].empty();
+        while (issued < 16 && 4 * (issued + 1) <= dead0) os << "    QCUT_PF_LOAD(" << issued++ << ", c);\n";
+      }
+      for (size_t i = 0; i < order.size(); ++i) {
+        const uint32_t t = order[i];
+        os << "    x = qp";
+        for (uint32_t byte = 0; byte < 8; ++byte)
+          for (uint32_t bit = 0; bit < 8; ++bit)
+            if ((em.row(t)[byte] >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
+        os << ";\n    c = (uint32_t)__popc(x);\n";
+        em.count(t, "c", false);
+        while (issued < 16 && 4 * (issued + 1) <= dead_after[i]) os << "    QCUT_PF_LOAD(" << issued++ << ", c);\n";
+      }
+      while (issued < 16) os << "    QCUT_PF_LOAD(" << issued++ << ", c);\n";
+      os << "  }\n";
+    }
+  }
+  // Counters in shared memory (qcut_lane_tile_sacc): packed register r = t % NACC, field t / NACC as everywhere else;
+  // the sixteen terms of registers 4g .. 4g+3 are evaluated together between one 128-bit load and one store of group g.
+  // Terms are built from scratch, so only offered for sparse masks on rows of up to 8 bytes.
+  bool sacc = false;
+  if (nb <= 8 && sacc_out) {
+    size_t lop3 = 0;
+    for (uint32_t t = 0; t < T; ++t) lop3 += (size_t)(em.weight(t, 0, nb) + 1) / 2;
+    sacc = lop3 <= (size_t)T * 2;
+    if (sacc) {
+      os << "  static QCUT_MDEV void run_sacc(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, const uint32_t qp,\n"
+            "                                 const QcutSacc S) {\n    (void)Q;\n    uint32_t x;\n    qcut_u4 q;\n";
+      static const char* const word[4] = {"q.x", "q.y", "q.z", "q.w"};
+      for (uint32_t g = 0; 4 * g < nacc; ++g) {
+        os << "    q = S.ld4(" << g << ");\n";
+        for (uint32_t f = 0; f < 4; ++f)
+          for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t r = 4 * g + j, t = f * nacc + r;
+            if (r >= nacc || t >= T) continue;
+            os << "    x = qp";
+            for (uint32_t byte = 0; byte < nb; ++byte)
+              for (uint32_t bit = 0; bit < 8; ++bit)
+                if ((em.row(t)[byte] >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
+            os << ";\n    " << word[j] << " += (uint32_t)__popc(x)";
+            if (f) os << " << " << 8 * f;
+            os << ";\n";
+          }
+        os << "    S.st4(" << g << ", q);\n";
+      }
+      os << "  }\n";
+    }
+  }
+  // 8-byte rows, sparse masks: Q arrives as the raw ROWS of block 1 and its transposition (80 pair operations, ALU and
+  // FMA pipes) is spread between the terms that live in block 0 (XU pipe); the terms of block 1 and the few terms that
+  // straddle the blocks follow (qcut_lane_tile_il).
+  bool il = false;
+  if (nb == 8 && il_out) {
+    size_t lop3 = 0;
+    for (uint32_t t = 0; t < T; ++t) lop3 += (size_t)(em.weight(t, 0, nb) + 1) / 2;
+    std::vector<uint32_t> t0, t1;
+    for (uint32_t t = 0; t < T; ++t) (em.weight(t, 4, 8) == 0 ? t0 : t1).push_back(t);
+    il = lop3 <= (size_t)T * 2 && t0.size() >= 16;
+    if (il) {
+      os << "  static QCUT_MDEV void run_il(const uint32_t* __restrict__ P, uint32_t* __restrict__ Q, const uint32_t qp,\n"
+            "                               uint32_t* __restrict__ acc) {\n    uint32_t x;\n";
+      std::vector<std::string> tp;  // the 80 pair operations of the transposition of Q, stage by stage
+      for (int d : {16, 8, 4, 2, 1})
+        for (int j = 0; j < 32; ++j)
+          if (!(j & d)) tp.push_back("    qcut_tp<" + std::to_string(d) + ">(Q, " + std::to_string(j) + ");\n");
+      auto term = [&](uint32_t t) {
+        os << "    x = qp";
+        for (uint32_t byte = 0; byte < 8; ++byte)
+          for (uint32_t bit = 0; bit < 8; ++bit)
+            if ((em.row(t)[byte] >> bit) & 1u) os << " ^ " << plane_name(nb, byte, bit);
+        os << ";\n";
+        em.count(t, "x");
+      };
+      size_t done = 0;
+      for (size_t i = 0; i < t0.size(); ++i) {
+        term(t0[i]);
+        const size_t upto = (i + 1) * tp.size() / t0.size();
+        for (; done < upto; ++done) os << tp[done];
+      }
+      for (uint32_t t : t1) term(t);
+      os << "  }\n";
+    }
+  }
+  os << "  static const int IL = " << (il ? 1 : 0) << ";\n";
+  if (il_out) *il_out = il;
+  os << "  static const int SACC = " << (sacc ? 1 : 0) << ";\n";
+  if (sacc_out) *sacc_out = sacc;
+  os << "  static const int PIPE = " << (pipe ? 1 : 0) << ";\n";
+  if (pipe_out) *pipe_out = pipe;
   os << "};\n\n";
   return split;
 }
@@ -214,12 +348,23 @@ std::string generate_multi_source(const std::vector<const qcut_group_desc*>& gds
 
 // The translation unit for one group.  Pure host code.
 std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out,
-                                   bool staged, int threads, int prefetch, bool allow_split, bool* split_out) {
+                                   bool staged, int threads, int prefetch, bool allow_split, bool* split_out,
+                                   bool allow_pipe, bool* pipe_out, bool allow_sacc, bool* sacc_out) {
   if (!jit_supports(gd)) return std::string();
   const uint32_t T = gd.n_terms, nb = gd.nb_obs;
   std::ostringstream terms;
-  const bool split = emit_terms(terms, "Terms", gd, masks) && allow_split && !staged && prefetch == 0;
+  bool pipe = false, sacc = false, il = false;
+  const bool plain = !staged && prefetch == 0 && !allow_split;
+  const char* env_il = std::getenv("QCUT_JIT_IL");
+  const bool want_il = plain && env_il && *env_il && std::atoi(env_il) != 0;
+  const bool want_pipe = allow_pipe && plain && !allow_sacc && !want_il;
+  const bool want_sacc = allow_sacc && plain && !want_il;
+  const bool split = emit_terms(terms, "Terms", gd, masks, want_pipe ? &pipe : nullptr, want_sacc ? &sacc : nullptr,
+                                want_il ? &il : nullptr) &&
+                     allow_split && !staged && prefetch == 0;
   if (split_out) *split_out = split;
+  if (pipe_out) *pipe_out = pipe;
+  if (sacc_out) *sacc_out = sacc;
   // Register budget: 32 per live block + packed counters + ~28 of addressing / temporaries.
   const int budget = ((nb > 4 && !split) ? 64 : 32) + (int)((T + 3) / 4) + 28;
   int min_blocks = budget > 128 ? 1 : 2;
@@ -239,6 +384,7 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
     const int phases = env_ph && *env_ph ? std::atoi(env_ph) : 1;
     os << "#define QCUT_SPLIT_PHASES " << (phases == 2 || phases == 4 ? phases : 1) << "\n";
   }
+  os << "#define QCUT_SACC_STRIDE " << 16 * threads << "\n";
   os << kPrelude << "\n";
   os << terms.str();
   if (nb > 8) {
@@ -307,6 +453,41 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
           "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
           "  }\n"
           "}\n";
+  } else if (sacc) {
+    // Packed counters in the thread's column of a shared-memory array (16 * threads bytes per group of 4 counters).
+    os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  extern __shared__ __align__(16) uint32_t qcut_smem[];\n"
+          "  const int lane = threadIdx.x & 31;\n"
+          "  const QcutSacc S = {(uint32_t)__cvta_generic_to_shared(qcut_smem) + 16u * threadIdx.x};\n"
+          "  qcut_sacc_clear<Terms::NACC>(S);\n"
+          "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+          "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
+          "       tile += n_warps) {\n"
+          "    const QcutTile te = tiles[tile];\n"
+          "    const QcutPub pub = pubs[te.pub];\n"
+          "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+          "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+          "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
+          "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "    qcut_lane_tile_sacc<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, S);\n"
+          "    uint32_t acc[Terms::NACC];\n"
+          "    qcut_sacc_take<Terms::NACC>(S, acc);\n"
+          "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
+          "  }\n"
+          "}\n";
+  } else if (pipe) {
+    // Register-level software pipeline: the loads of the next step (or of the first step of the warp's next tile)
+    // are issued from inside the term network as bit-planes die (qcut_warp_pipe).
+    os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  const int lane = threadIdx.x & 31;\n"
+          "  qcut_warp_pipe<Terms>(data, pubs, tiles, n_tiles, (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),\n"
+          "                        (int64_t)gridDim.x * (blockDim.x >> 5), tallies, lane);\n"
+          "}\n";
   } else if (staged) {
     // Bulk-copy staged stream: one staging buffer + one mbarrier per warp in dynamic shared memory.
     os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
@@ -342,6 +523,8 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
             "    uint32_t acc[Terms::NACC];\n";
       if (prefetch == 1)
         os << "    qcut_lane_tile_pf<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc, obs, qpd, 1, 0);\n";
+      else if (il)
+        os << "    qcut_lane_tile_il<Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n";
       else
         os << "    qcut_lane_tile<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n";
       os << "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
@@ -391,11 +574,28 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   if (split)
     os << "  static uint32_t park[32 * 32];\n"
           "  qcut_lane_tile_split<Terms>(obs, qpd, nbq, ns, lane, acc, park + lane);\n";
+  else if (il)
+    os << "  qcut_lane_tile_il<Terms>(obs, qpd, nbq, ns, lane, acc);\n";
+  else if (sacc)
+    os << "  static uint32_t column[4 * ((Terms::NACC + 3) / 4)];\n"
+          "  const QcutSacc S = {column};\n"
+          "  qcut_sacc_clear<Terms::NACC>(S);\n"
+          "  qcut_lane_tile_sacc<Terms::NB, Terms>(obs, qpd, nbq, ns, lane, S);\n"
+          "  qcut_sacc_take<Terms::NACC>(S, acc);\n";
   else
     os << "  qcut_lane_tile<Terms::NB, Terms>(obs, qpd, nbq, ns, lane, acc);\n";
   os << "  for (int t = 0; t < Terms::T; ++t) odd_out[t] = (acc[t % Terms::NACC] >> (8 * (t / Terms::NACC))) & 0xFFu;\n"
         "  return Terms::T;\n"
-        "}\n"
+        "}\n";
+  // one lane of a whole warp stream (tiles first, first + stride, ...): tallies accumulate as on the device
+  os << "extern \"C\" int qcut_emu_lane_stream(const uint8_t* data, const void* pubs, const void* tiles, long long n_tiles,\n"
+        "                                    long long first, long long stride, int lane, unsigned long long* tallies) {\n";
+  if (pipe)
+    os << "  qcut_warp_pipe<Terms>(data, (const QcutPub*)pubs, (const QcutTile*)tiles, n_tiles, first, stride, tallies, lane);\n"
+          "  return 1;\n";
+  else
+    os << "  return 0;\n";
+  os << "}\n"
         "// run-time-mask engine, one lane of one tile (planes parked in a per-lane column)\n"
         "template <int NB> static int qcut_emu_rt(const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
         "                                         const uint32_t* mw, int n_words, int T, uint32_t* odd_out) {\n"
@@ -586,8 +786,20 @@ int jit_build(qcut_plan* plan, bool load) {
     // off by default: measured slower on B200 (cfg4: 0.71 of HBM at 256x2, 0.60-0.66 with 3-5 CTAs per SM vs 0.76 for
     // the all-at-once form -- the extra warps do not pay for the spills of the packed counters)
     const bool allow_split = env_split && *env_split && std::atoi(env_split) != 0;
+    // Experimental engines, all measured on B200 and all within a few per cent BELOW the all-at-once engine on cfg4
+    // (0.757 of the copy peak): QCUT_JIT_PIPE=1 loads of the next step issued from inside the term network (0.73: the
+    // step still waits for its LAST load, ncu long_scoreboard 1.39 -> 1.73), QCUT_JIT_SACC=1 packed counters in shared
+    // memory (0.726 at 16 warps/SM, 0.754 at 20, 0.738 at 24), QCUT_JIT_IL=1 transposition of block 1 interleaved with the
+    // terms of block 0 (0.745).  scripts/micro/ holds the two measurements that explain it: the memory system delivers
+    // 7.3 TB/s to this access pattern, and with the rows in L2 the kernel is only 5 % faster -- it is bound by
+    // instruction issue at 16 warps per SM, not by HBM.  Off by default; kept with their emulation tests.
+    const char* env_pipe = std::getenv("QCUT_JIT_PIPE");
+    const bool allow_pipe = env_pipe && *env_pipe && std::atoi(env_pipe) != 0;
+    // packed counters in shared memory (sparse masks, rows of up to 8 bytes); QCUT_JIT_SACC=1: on
+    const char* env_sacc = std::getenv("QCUT_JIT_SACC");
+    const bool allow_sacc = env_sacc && *env_sacc && std::atoi(env_sacc) != 0;
     jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads, prefetch,
-                                       allow_split, &jk.split);
+                                       allow_split, &jk.split, allow_pipe, &jk.pipe, allow_sacc, &jk.sacc);
     rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
   };
   std::atomic<size_t> next{0};
@@ -627,6 +839,12 @@ int jit_build(qcut_plan* plan, bool load) {
       jk.threads = 32 * warps;
       jk.min_blocks = 2;
       jk.smem_bytes = warps * (32 * (4 * jk.nb_obs + 1) + blocks * 32 * 32) * 4;
+      int dev = 0;
+      QCUT_CUDA(cudaGetDevice(&dev));
+      QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));
+    } else if (jk.sacc) {
+      // one 16-byte slot per thread and group of 4 packed counters
+      jk.smem_bytes = 16 * jk.threads * (int)(((plan->groups[jk.group].n_terms + 3) / 4 + 3) / 4);
       int dev = 0;
       QCUT_CUDA(cudaGetDevice(&dev));
       QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));
@@ -688,8 +906,12 @@ size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const
   const qcut_group_desc& gd = h_groups[group];
   if ((size_t)gd.mask_offset + (size_t)gd.n_terms * gd.nb_obs > mask_bytes) return 0;
   const char* env_split = std::getenv("QCUT_JIT_SPLIT");
+  const char* env_pipe = std::getenv("QCUT_JIT_PIPE");
+  const char* env_sacc = std::getenv("QCUT_JIT_SACC");
   const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, false, 256, 0,
-                                                       env_split && *env_split && std::atoi(env_split) != 0, nullptr);
+                                                       env_split && *env_split && std::atoi(env_split) != 0, nullptr,
+                                                       env_pipe && *env_pipe && std::atoi(env_pipe) != 0, nullptr,
+                                                       env_sacc && *env_sacc && std::atoi(env_sacc) != 0, nullptr);
   if (src.empty()) return 0;
   if (buf && buf_len) {
     const size_t n = src.size() < buf_len - 1 ? src.size() : buf_len - 1;

@@ -555,6 +555,252 @@ QCUT_DEV void qcut_lane_tile_split(const uint8_t* __restrict__ obs, const uint8_
   }
 }
 
+// ---- term engine A'', 8-byte rows: the loads of the NEXT step ride inside the term network ("pipe") ----------
+// The all-at-once engine issues the 16 loads of a step, waits for HBM (ncu: long_scoreboard is one of the two top
+// stalls, every warp idles a full memory round trip per step) and only then computes; there is no register left to
+// load a step ahead (64 planes + packed counters = 128).  But the planes DIE one after the other while the terms
+// are evaluated: the generator (jit.cu) orders the terms so that bit-planes are finished as early as possible
+// (min-degree elimination over the plane/term incidence) and writes one 16-byte load of the next step into the
+// generated code as soon as four more registers are free (QCUT_PF_LOAD).  The rows of step s+1 -- the first step of
+// the warp's next tile when the tile ends -- are therefore in flight while the terms of step s are evaluated, at no
+// cost in registers, shared memory or instructions.  One flat loop over the warp's steps.
+// The load is tied to the popcount `c` of the term evaluated just before it (predicate c < pfv with pfv = 64 when the
+// next step is to be loaded and 0 otherwise; a popcount never exceeds 32): without a real dependence ptxas gathers all
+// sixteen loads in one place and spills the planes that are still live there.
+#ifndef QCUT_HOST_EMU
+QCUT_DEV void qcut_pf_load(const uint8_t* p, uint32_t pfv, uint32_t c, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %5, %6;\n\t"
+      "@q ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+r"(x), "+r"(y), "+r"(z), "+r"(w) : "l"(p), "r"(c), "r"(pfv));
+}
+#else
+QCUT_DEV void qcut_pf_load(const uint8_t* p, uint32_t pfv, uint32_t c, uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& w) {
+  if (c < pfv) { const qcut_u4 v = qcut_ld16(p); x = v.x; y = v.y; z = v.z; w = v.w; }
+}
+#endif
+#define QCUT_PF_LOAD(k, c) qcut_pf_load(nsrc + (k) * 512, pfv, (c), NA[2 * (k)], NA[32 + 2 * (k)], NA[2 * (k) + 1], NA[33 + 2 * (k)])
+
+#ifdef QCUT_HOST_EMU
+// emulation of the warp-level flush for one lane: tally[t] += ns (once per warp) - 2 * (#odd shots of this lane)
+template <int T>
+QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long long* tally) {
+  constexpr int NACC = (T + 3) / 4;
+  for (int t = 0; t < T; ++t) {
+    const long long odd = (acc[t % NACC] >> (8 * (t / NACC))) & 0xFFu;
+    tally[t] += (unsigned long long)((lane == 0 ? (long long)ns : 0ll) - 2ll * odd);
+  }
+}
+#else
+template <int T>
+QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long long* __restrict__ tally);
+#endif
+
+template <class Terms>
+QCUT_DEV void qcut_warp_pipe(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,
+                             const QcutTile* __restrict__ tiles, const int64_t n_tiles, int64_t tile,
+                             const int64_t tile_stride, unsigned long long* __restrict__ tallies, int lane) {
+  typedef QcutGeo<8> G;
+  if (tile >= n_tiles) return;
+  uint32_t acc[Terms::NACC];
+#pragma unroll
+  for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+  uint32_t a[2][32];
+  bool have = false;  // a[][] already holds the rows of the current step (loaded during the previous one)
+  QcutTile te = tiles[tile];
+  QcutPub pub = pubs[te.pub];
+  int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;
+  int ns = (int)(((int64_t)pub.shots - shot0 < QCUT_TILE_SHOTS) ? (int64_t)pub.shots - shot0 : QCUT_TILE_SHOTS);
+  int nbq = (int)pub.nb_qpd;
+  const uint8_t* obs = data + pub.obs_offset + (uint64_t)shot0 * 8;
+  const uint8_t* qpd = data + pub.qpd_offset + (uint64_t)shot0 * nbq;
+  int s0 = 0;
+  for (;;) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    const bool full = n == G::STEP_SHOTS;
+    const uint8_t* obs_s = obs + (uint64_t)s0 * 8;
+    const uint8_t* qpd_s = qpd + (uint64_t)s0 * nbq;
+    const int rest = ns - s0 - G::STEP_SHOTS;
+    const bool last = rest <= 0;
+    // the step after this one: the next step of the tile, or the first step of the warp's next tile
+    const uint8_t* n_obs = obs_s + G::STEP_SHOTS * 8;
+    bool pf = rest >= G::STEP_SHOTS;  // only full steps are loaded ahead (tails take the predicated path)
+    if (last && tile + tile_stride < n_tiles) {
+      const QcutTile te_n = tiles[tile + tile_stride];
+      const QcutPub pub_n = pubs[te_n.pub];
+      const int64_t shot0_n = (int64_t)te_n.tile_in_pub * QCUT_TILE_SHOTS;
+      n_obs = data + pub_n.obs_offset + (uint64_t)shot0_n * 8;
+      pf = (int64_t)pub_n.shots - shot0_n >= G::STEP_SHOTS;
+    }
+    const QcutSrcGlobal src = {obs_s, qpd_s};
+    if (!have) {
+      if (full) qcut_step_loads<8, true, QcutSrcGlobal>(src, n, lane, a);
+      else qcut_step_loads<8, false, QcutSrcGlobal>(src, n, lane, a);
+    }
+    uint32_t qp[1];
+    if (nbq == 1) {
+      uint32_t qraw[G::QRAW];
+      if (full) qcut_qpd_loads<8, true, QcutSrcGlobal>(src, n, lane, qraw);
+      else qcut_qpd_loads<8, false, QcutSrcGlobal>(src, n, lane, qraw);
+      qcut_qpd_planes<8>(qraw, qp);
+    } else {
+      qp[0] = 0;
+      qcut_qp_slow<8>(qpd_s, nbq, n, lane, qp);
+    }
+    qcut_transpose32(a[0]);
+    qcut_transpose32(a[1]);
+    if (!full) qcut_mask_tail<8>(n, lane, a, qp);
+    uint32_t na[2][32];
+#ifdef QCUT_HOST_EMU
+    memset(na, 0, sizeof na);
+#else
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { na[0][j] = a[0][j]; na[1][j] = a[1][j]; }  // "undefined": any register will do
+#endif
+    Terms::run_pf(a[0], a[1], qp[0], acc, n_obs + lane * 16, pf ? 64u : 0u, &na[0][0]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { a[0][j] = na[0][j]; a[1][j] = na[1][j]; }
+    have = pf;
+    if (!last) {
+      s0 += G::STEP_SHOTS;
+      continue;
+    }
+    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);
+#pragma unroll
+    for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+    tile += tile_stride;
+    if (tile >= n_tiles) break;
+    te = tiles[tile];
+    pub = pubs[te.pub];
+    shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;
+    ns = (int)(((int64_t)pub.shots - shot0 < QCUT_TILE_SHOTS) ? (int64_t)pub.shots - shot0 : QCUT_TILE_SHOTS);
+    nbq = (int)pub.nb_qpd;
+    obs = data + pub.obs_offset + (uint64_t)shot0 * 8;
+    qpd = data + pub.qpd_offset + (uint64_t)shot0 * nbq;
+    s0 = 0;
+  }
+}
+
+// ---- term engine A3, rows of up to 8 bytes: packed counters in shared memory ("sacc") ---------------------------
+// With 64 bit-planes and ceil(T / 4) packed counters in registers the all-at-once engine sits at the 128-register
+// cap: ptxas keeps a dozen counters on the stack and has two or three temporaries left, so that in the transposition
+// every LOP3 follows the IMAD shift it depends on at a distance of two issue slots (ncu: `wait` is the top stall).
+// Here the counters of a tile live in the thread's private column of a shared-memory array ([group of 4 counter
+// words][thread], one 128-bit access per 16 terms, conflict free); the generated network (Terms::run_sacc) loads a
+// group, adds the sixteen popcounts of its terms, stores it back.  18 extra LSU instructions per step for cfg4
+// (1.5 %), ~30 registers handed back to the scheduler.
+#ifndef QCUT_SACC_STRIDE
+#define QCUT_SACC_STRIDE 4096  // bytes between two groups of one thread = 16 * threads per CTA (set by the generator)
+#endif
+struct QcutSacc {
+#ifndef QCUT_HOST_EMU
+  uint32_t base;  // shared-window address of this thread's 16 bytes of group 0
+  QCUT_MDEV qcut_u4 ld4(int g) const {
+    qcut_u4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + g * QCUT_SACC_STRIDE));
+    return v;
+  }
+  QCUT_MDEV void st4(int g, qcut_u4 v) const {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(base + g * QCUT_SACC_STRIDE), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+#else
+  uint32_t* base;
+  QCUT_MDEV qcut_u4 ld4(int g) const { qcut_u4 v; memcpy(&v, base + 4 * g, 16); return v; }
+  QCUT_MDEV void st4(int g, qcut_u4 v) const { memcpy(base + 4 * g, &v, 16); }
+#endif
+};
+
+template <int NACC>
+QCUT_DEV void qcut_sacc_clear(const QcutSacc S) {
+  const qcut_u4 z = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int g = 0; g < (NACC + 3) / 4; ++g) S.st4(g, z);
+}
+
+// counters of the finished tile -> registers (for qcut_flush), shared-memory copy cleared for the next tile
+template <int NACC>
+QCUT_DEV void qcut_sacc_take(const QcutSacc S, uint32_t* acc) {
+  const qcut_u4 z = {0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int g = 0; g < (NACC + 3) / 4; ++g) {
+    const qcut_u4 v = S.ld4(g);
+    if (4 * g < NACC) acc[4 * g] = v.x;
+    if (4 * g + 1 < NACC) acc[4 * g + 1] = v.y;
+    if (4 * g + 2 < NACC) acc[4 * g + 2] = v.z;
+    if (4 * g + 3 < NACC) acc[4 * g + 3] = v.w;
+    S.st4(g, z);
+  }
+}
+
+// same contract as qcut_lane_tile, counters in S (cleared on entry by the previous qcut_sacc_take / qcut_sacc_clear)
+template <int NB, class Terms>
+QCUT_DEV void qcut_lane_tile_sacc(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns, int lane,
+                                  const QcutSacc S) {
+  typedef QcutGeo<NB> G;
+  for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    uint32_t a[G::BLOCKS][32];
+    uint32_t qp[G::BATCHES];
+    qcut_step_any<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
+#pragma unroll
+    for (int u = 0; u < G::BATCHES; ++u) Terms::run_sacc(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], S);
+  }
+}
+
+// ---- pieces of the 32x32 transposition, one pair of rows at a time ---------------------------------------------------
+// qcut_tp<D>(a, j) exchanges the off-diagonal DxD bit blocks of rows j and j + D.  The five stages D = 16, 8, 4, 2, 1
+// swap five different bits of the row index with five different bits of the bit index, so they commute: any order
+// gives qcut_transpose32.  The generator uses them to interleave the transposition of one block with the term network
+// of another (Terms::run_il): the transposition keeps the ALU and FMA pipes busy, the terms the XU pipe (POPC issues at a
+// quarter rate), and a warp that does one after the other leaves one of them idle.
+template <int D>
+QCUT_DEV void qcut_tp(uint32_t* a, int j) {
+  const uint32_t x = a[j], y = a[j + D];
+  if constexpr (D == 16) {
+    a[j] = __byte_perm(x, y, 0x5410);
+    a[j + D] = __byte_perm(x, y, 0x7632);
+  } else if constexpr (D == 8) {
+    a[j] = __byte_perm(x, y, 0x6240);
+    a[j + D] = __byte_perm(x, y, 0x7351);
+  } else if constexpr (D == 4) {
+    a[j] = qcut_sel<0x0F0F0F0Fu>(x, y << 4);
+    a[j + D] = qcut_sel<0x0F0F0F0Fu>(qcut_shr<4>(x), y);
+  } else if constexpr (D == 2) {
+    a[j] = qcut_sel<0x33333333u>(x, y << 2);
+    a[j + D] = qcut_sel<0x33333333u>(qcut_shr<2>(x), y);
+  } else {
+    a[j] = qcut_sel<0x55555555u>(x, y << 1);
+    a[j + D] = qcut_sel<0x55555555u>(qcut_shr<1>(x), y);
+  }
+}
+
+// ---- term engine A4, 8-byte rows: transposition of block 1 interleaved with the terms of block 0 ("il") ---------------
+template <class Terms>
+QCUT_DEV void qcut_lane_tile_il(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns, int lane,
+                                uint32_t* acc) {
+  typedef QcutGeo<8> G;
+#pragma unroll
+  for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+  for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    const uint8_t* __restrict__ qpd_s = qpd + (uint64_t)s0 * nbq;
+    const QcutSrcGlobal src = {obs + (uint64_t)s0 * 8, qpd_s};
+    uint32_t a[2][32];
+    uint32_t qp[1];
+    if (n == G::STEP_SHOTS && nbq == 1) {
+      qcut_step_loads<8, true, QcutSrcGlobal>(src, n, lane, a);
+      uint32_t qraw[G::QRAW];
+      qcut_qpd_loads<8, true, QcutSrcGlobal>(src, n, lane, qraw);
+      qcut_qpd_planes<8>(qraw, qp);
+      qcut_transpose32(a[0]);
+      Terms::run_il(a[0], a[1], qp[0], acc);
+    } else {
+      qcut_step_src<8, QcutSrcGlobal>(src, qpd_s, nbq, n, lane, a, qp);
+      Terms::run(a[0], a[1], qp[0], acc);
+    }
+  }
+}
+
 // ---- wide rows (9..32 bytes): rows staged through shared memory, bit-planes parked in shared memory ----
 // Up to 128 bit-planes do not fit the register file, so the blocks are transposed one at a time and the
 // planes are parked in shared memory ([plane][lane], conflict free); the generated term code then reads

@@ -47,6 +47,9 @@ def compile_emulator(source: str) -> C.CDLL:
     lib = C.CDLL(str(so))
     lib.qcut_emu_lane_tile.restype = C.c_int
     lib.qcut_emu_lane_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    if hasattr(lib, "qcut_emu_lane_stream"):  # rows of up to 8 bytes only
+        lib.qcut_emu_lane_stream.restype = C.c_int
+        lib.qcut_emu_lane_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]
     lib.qcut_emu_rt_lane_tile.restype = C.c_int
     lib.qcut_emu_rt_lane_tile.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return lib

@@ -157,3 +157,78 @@ def test_emulated_split_engine_for_8_byte_rows(lib, monkeypatch, shots):
     assert covered.all() and np.array_equal(got, want)
     monkeypatch.delenv("QCUT_JIT_SPLIT")
     assert "qcut_lane_tile_split<Terms>" not in _lib.generate_source(tables.groups, tables.masks, 0).split("extern \"C\"", 1)[1]
+
+
+def _heavy_hex_like_labels(n=63):
+    """Single-Z on every qubit, ZZ on a chain plus a few longer bonds (two straddle the halves of the row), identity."""
+    labels = ["".join("Z" if n - 1 - i == q else "I" for i in range(n)) for q in range(n)]
+    bonds = [(q, q + 1) for q in range(0, n - 1, 1)] + [(2, 17), (9, 40), (20, 35), (45, 60), (31, 32)]
+    labels += ["".join("Z" if n - 1 - i in ab else "I" for i in range(n)) for ab in bonds]
+    labels.append("I" * n)
+    return labels
+
+
+@pytest.mark.parametrize("n_warps", [1, 3])
+def test_emulated_pipelined_stream_for_8_byte_rows(lib, monkeypatch, n_warps):
+    """QCUT_JIT_PIPE=1 (experimental, off by default).  The register-level software pipeline (qcut_warp_pipe): a warp walks its tiles first, first + stride, ... as one
+    flat stream of steps and the rows of the next step -- or of the first step of its next tile -- are loaded from
+    inside the term network.  PUBs with full tiles, ragged tails, a single shot, no shots; several warps."""
+    monkeypatch.setenv("QCUT_JIT_PIPE", "1")
+    observables = {"A": PauliList(_heavy_hex_like_labels())}
+    shots_per_pub = [8192, 5000, 1, 4096, 1024, 0, 3071, 12289, 2048]
+    coefficients = [(1.0, WeightType.EXACT)] * len(shots_per_pub)
+    rng = np.random.default_rng(7)
+    pubs = []
+    for i, shots in enumerate(shots_per_pub):
+        one = _cases.make_results(observables, 1, shots, 1 + (i % 3 == 2) * 8, seed=100 + i)
+        pubs.append(one["A"][0])
+    results = {"A": PrimitiveResult(pubs)}
+    tables, data, want = _stage_host(results, coefficients, observables)
+    source = _lib.generate_source(tables.groups, tables.masks, 0)
+    assert "PIPE = 1" in source and "qcut_warp_pipe<Terms>" in source.split("extern \"C\"", 1)[1]
+    emu = _host_emu.compile_emulator(source)
+    tiles = np.array([(p, t) for p, pub in enumerate(tables.pubs) for t in range(-(-int(pub["shots"]) // _lib.TILE_SHOTS))],
+                     dtype=np.uint32)
+    mm, guarded = _guarded_copy(data, tables.data_bytes)
+    got = np.zeros(tables.n_tallies, dtype=np.uint64)
+    pub_table = np.ascontiguousarray(tables.pubs)
+    for warp in range(n_warps):
+        for lane in range(32):
+            assert emu.qcut_emu_lane_stream(guarded.ctypes.data, pub_table.ctypes.data, tiles.ctypes.data, len(tiles), warp,
+                                            n_warps, lane, got.ctypes.data) == 1
+    assert np.array_equal(got.view(np.int64), want)
+    del guarded
+    # dense masks: the pipelined form is not offered (every term would be built from scratch)
+    dense = {"A": _cases.random_paulis(np.random.default_rng(1), 40, 64, 20, 40, "Z")}
+    t2, _, _ = _stage_host(_cases.make_results(dense, 1, 10, 1, seed=1), [(1.0, WeightType.EXACT)], dense)
+    assert "PIPE = 0" in _lib.generate_source(t2.groups, t2.masks, 0)
+
+
+@pytest.mark.parametrize("nbits,shots", [(63, 8192), (63, 1500), (30, 4097), (12, 6200), (7, 9000), (44, 1)])
+def test_emulated_shared_memory_counters(lib, monkeypatch, nbits, shots):
+    """QCUT_JIT_SACC=1: the packed counters of a tile live in the thread's column of a shared-memory array, sixteen terms
+    per 128-bit load / store (sparse masks, rows of up to 8 bytes)."""
+    monkeypatch.setenv("QCUT_JIT_SACC", "1")
+    labels = _heavy_hex_like_labels(63)
+    observables = {"A": PauliList(sorted({lab[63 - nbits:] for lab in labels}))}
+    results = _cases.make_results(observables, 1, shots, 2, seed=shots + nbits)
+    tables, data, want = _stage_host(results, [(1.0, WeightType.EXACT)], observables)
+    source = _lib.generate_source(tables.groups, tables.masks, 0)
+    assert "SACC = 1" in source and "qcut_lane_tile_sacc<Terms::NB, Terms>" in source.split("extern \"C\"", 1)[1]
+    got, covered = _host_emu.emulate_tallies(tables, data, "jit")
+    assert covered.all() and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shots", [1, 1024, 1500, 4097, 8192])
+def test_emulated_interleaved_engine_for_8_byte_rows(lib, monkeypatch, shots):
+    """QCUT_JIT_IL=1: the transposition of block 1 is spread, one pair of rows at a time, between the terms of block 0
+    (the five stages commute, qcut_tp); full steps take that path, tails and wide qpd rows the all-at-once one."""
+    monkeypatch.setenv("QCUT_JIT_IL", "1")
+    observables = {"A": PauliList(_heavy_hex_like_labels())}
+    for qbits in (3, 11):
+        results = _cases.make_results(observables, 1, shots, qbits, seed=shots + qbits)
+        tables, data, want = _stage_host(results, [(1.0, WeightType.EXACT)], observables)
+        source = _lib.generate_source(tables.groups, tables.masks, 0)
+        assert "IL = 1" in source and "qcut_lane_tile_il<Terms>" in source.split("extern \"C\"", 1)[1]
+        got, covered = _host_emu.emulate_tallies(tables, data, "jit")
+        assert covered.all() and np.array_equal(got, want)

@@ -772,8 +772,14 @@ int jit_build(qcut_plan* plan, bool load) {
       rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
       return;
     }
-    jk.staged = (plan->flags & QCUT_PLAN_STAGED) != 0;
     jk.nb_obs = (int)plan->groups[jk.group].nb_obs;
+    // Bulk-copy staging (one step ahead through shared memory) pays where the kernel waits on memory instead of on
+    // instruction issue: rows narrower than 8 bytes with few terms (cfg3 "local": 0.747 -> 0.782 of the copy peak;
+    // cfg5 unchanged; cfg4, 8-byte rows x 134 terms: 7 % slower, so not there).  QCUT_JIT_AUTO_STAGED=0 switches the rule off.
+    const char* env_as = std::getenv("QCUT_JIT_AUTO_STAGED");
+    const bool auto_staged = !(env_as && *env_as && std::atoi(env_as) == 0) && jk.nb_obs < 8 &&
+                             plan->groups[jk.group].n_terms <= 32;
+    jk.staged = (plan->flags & QCUT_PLAN_STAGED) != 0 || auto_staged;
     // tuning knobs (experiments only): QCUT_JIT_THREADS (CTA size), QCUT_JIT_MINBLOCKS (launch bound)
     const char* env_threads = std::getenv("QCUT_JIT_THREADS");
     const char* env_blocks = std::getenv("QCUT_JIT_MINBLOCKS");

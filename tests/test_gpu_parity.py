@@ -76,7 +76,8 @@ def test_v1_case_bit_identical_to_reference(lib):
     assert _hex(out) == _hex(case["reference_expvals"])
 
 
-@pytest.mark.parametrize("flags", [0, _lib.PLAN_NO_JIT, _lib.PLAN_GENERIC_ONLY], ids=["jit", "sliced_rt", "generic"])
+@pytest.mark.parametrize("flags", [0, _lib.PLAN_NO_JIT, _lib.PLAN_GENERIC_ONLY, _lib.PLAN_STAGED],
+                         ids=["jit", "sliced_rt", "generic", "jit_staged"])
 @pytest.mark.parametrize("name", _golden.CASE_NAMES)
 def test_tallies_bit_exact_on_golden_cases(lib, name, flags):
     case = _golden.load_case(name)
@@ -114,6 +115,28 @@ def test_tallies_every_row_width(lib, nbits, qbits, shots):
     results = _cases.make_results(observables, 2, shots, qbits, seed=int(rng.integers(1 << 30)))
     _, got, want = _device_tallies(results, [(0.5, WeightType.EXACT), (-0.5, WeightType.EXACT)], observables)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("staged", [False, True])
+@pytest.mark.parametrize("nbits", [5, 12, 23, 32, 39, 48, 50, 64])
+def test_staged_stream_of_steps_matches_direct_loads(lib, monkeypatch, nbits, staged):
+    """The bulk-copy staged stream (one step ahead through shared memory, chosen automatically for narrow rows with few
+    terms, QCUT_PLAN_STAGED elsewhere) against the direct-load engine: every layout (1..8-byte rows), PUBs of many
+    tiles, ragged tails, a single shot and empty PUBs in between, wide qpd rows."""
+    monkeypatch.setenv("QCUT_JIT_AUTO_STAGED", "1" if staged else "0")
+    rng = np.random.default_rng(nbits)
+    observables = {"A": _cases.random_paulis(rng, 16, nbits, 1, min(nbits, 6), "Z")}
+    pubs = []
+    for i, shots in enumerate([9000, 1, 4096, 0, 12289, 1024, 5000, 3071]):
+        one = _cases.make_results(observables, 1, shots, 1 + 8 * (i % 4 == 3), seed=nbits * 100 + i)
+        pubs.append(one["A"][0])
+    results = {"A": PrimitiveResult(pubs)}
+    coefficients = [(1.0, WeightType.EXACT)] * len(pubs)
+    batch, got, want = _device_tallies(results, coefficients, observables, _lib.PLAN_STAGED if staged else 0)
+    assert np.array_equal(got, want)
+    source = batch.plan.source(_lib.KERNEL_JIT0)
+    if "qcut_variant_0" not in source:  # (fewer than 12 distinct terms share a multi-group kernel: direct loads)
+        assert ("qcut_warp_stream" in source.split('extern "C"', 1)[1]) == staged
 
 
 def test_rows_of_17_to_32_bytes_use_the_specialised_kernel(lib):

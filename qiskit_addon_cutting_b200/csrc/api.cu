@@ -64,6 +64,9 @@ constexpr uint32_t kJitMinTerms = 12;
 // Multi-group kernels: distinct mask sets per kernel, and how many such kernels a plan may have
 // (groups beyond that use the run-time-mask kernel).
 constexpr size_t kMultiVariants = 24;
+constexpr size_t kSwitchVariants = 64;    // = kMaxVariants of qcut_schedule_create
+constexpr size_t kSwitchMinSets = 4;      // fewer sets of one width share a mixed-width kernel (cfg3 "local": 0.785 vs 0.771)
+constexpr uint32_t kSwitchMaxTerms = 32;  // qcut_flush_rt: at most 8 packed counter registers
 constexpr size_t kMaxMultiKernels = 32;
 
 }  // namespace qcut
@@ -114,6 +117,43 @@ static void assign_jit_kernels(qcut_plan* plan) {
       auto ins = small.emplace(std::move(key), std::vector<int>());
       if (ins.second) small_sets.push_back(&ins.first->second);
       ins.first->second.push_back(g);
+    }
+    // Sets of at most kSwitchMaxTerms terms: one kernel per row width and kSwitchVariants sets, the networks behind a
+    // switch (generate_switch_source).  QCUT_JIT_SWITCH=0: the older one-function-per-group kernels for everything.
+    const char* env_sw = std::getenv("QCUT_JIT_SWITCH");
+    if (!(env_sw && *env_sw && std::atoi(env_sw) == 0)) {
+      std::vector<const std::vector<int>*> rest;
+      std::map<uint32_t, std::vector<const std::vector<int>*>> by_width;
+      for (const auto* set : small_sets) {
+        const qcut_group_desc& gd = h_groups[set->front()];
+        if (gd.n_terms <= kSwitchMaxTerms) by_width[gd.nb_obs].push_back(set);
+        else rest.push_back(set);
+      }
+      for (const auto& kv : by_width) {
+        const auto& sets_w = kv.second;
+        if (sets_w.size() < kSwitchMinSets) {  // a handful of sets of this width: not worth a kernel of their own
+          rest.insert(rest.end(), sets_w.begin(), sets_w.end());
+          continue;
+        }
+        for (size_t first = 0; first < sets_w.size(); first += kSwitchVariants) {
+          if (plan->jit.size() >= (size_t)(QCUT_MAX_JIT_KERNELS + kMaxMultiKernels)) {
+            for (size_t v = first; v < sets_w.size(); ++v) rest.push_back(sets_w[v]);
+            break;
+          }
+          JitKernel jk;
+          jk.inline_switch = true;
+          const size_t last = std::min(sets_w.size(), first + kSwitchVariants);
+          for (size_t v = first; v < last; ++v) {
+            jk.variants.push_back(sets_w[v]->front());
+            for (int g : *sets_w[v]) {
+              plan->groups_dev[g].kernel = KERNEL_JIT0 + (uint32_t)plan->jit.size();
+              plan->groups_dev[g].variant = (uint32_t)(v - first);
+            }
+          }
+          plan->jit.push_back(std::move(jk));
+        }
+      }
+      small_sets.swap(rest);
     }
     for (size_t first = 0; first < small_sets.size() && plan->jit.size() < (size_t)(QCUT_MAX_JIT_KERNELS + kMaxMultiKernels);
          first += kMultiVariants) {

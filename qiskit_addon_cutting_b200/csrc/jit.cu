@@ -346,6 +346,78 @@ std::string generate_multi_source(const std::vector<const qcut_group_desc*>& gds
   return os.str();
 }
 
+// One kernel for many small groups OF ONE ROW WIDTH (at most 32 terms each): loads, transposition and qpd parity plane
+// are written once, the groups' XOR networks (a handful of LOP3 / POPC / IMAD each) sit behind a switch on the variant
+// index of the tile's group, and the flush takes the number of terms at run time.  Compared with one __noinline__
+// function per group this keeps the code of the kernel small (ncu showed `no_instruction` stalls on the molecular
+// workload's kernels: 24 complete copies of the tile loop per kernel) and lets the whole kernel run as one staged
+// stream of steps (bulk copies one step ahead through shared memory), whatever group a tile belongs to.
+std::string generate_switch_source(const std::vector<const qcut_group_desc*>& gds, const uint8_t* masks, int threads,
+                                   int min_blocks, bool staged) {
+  std::ostringstream os;
+  const uint32_t nb = gds.front()->nb_obs;
+  uint32_t max_nacc = 1;
+  if (staged) os << "#define QCUT_WITH_VARIANTS 1\n";
+  os << kPrelude << "\n";
+  for (size_t v = 0; v < gds.size(); ++v) {
+    emit_terms(os, "Terms" + std::to_string(v), *gds[v], masks);
+    max_nacc = std::max(max_nacc, (gds[v]->n_terms + 3) / 4);
+  }
+  os << "#ifndef QCUT_HOST_EMU\n";
+  os << "__constant__ unsigned short qcut_variant_terms[" << gds.size() << "] = {";
+  for (size_t v = 0; v < gds.size(); ++v) os << (v ? ", " : "") << gds[v]->n_terms;
+  os << "};\n";
+  os << "struct Net {\n"
+        "  static const int NB = " << nb << ";\n"
+        "  static const int NACC = " << max_nacc << ";\n"
+        "  static const bool MULTI = true;\n"
+        "  static QCUT_MDEV void run(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, const uint32_t qp,\n"
+        "                            uint32_t* __restrict__ acc, const int variant) {\n"
+        "    switch (variant) {\n";
+  for (size_t v = 0; v < gds.size(); ++v) os << "      case " << v << ": Terms" << v << "::run(P, Q, qp, acc); break;\n";
+  os << "      default: break;\n    }\n  }\n"
+        "  static QCUT_MDEV void flush(const uint32_t* acc, int ns, int lane, unsigned long long* __restrict__ tally, const int variant) {\n"
+        "    const int T = qcut_variant_terms[variant];\n"
+        "    qcut_flush_rt<NACC>(acc, T, (T + 3) >> 2, ns, lane, tally);\n"
+        "  }\n"
+        "};\n";
+  os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n"
+        "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+        "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+        "                  unsigned long long* __restrict__ tallies, const QcutGroup* __restrict__ groups) {\n";
+  if (staged) {
+    os << "  extern __shared__ __align__(128) uint8_t qcut_smem[];\n"
+          "  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;\n"
+          "  const int n_warps_cta = blockDim.x >> 5;\n"
+          "  uint8_t* stage = qcut_smem + (size_t)warp * QcutStage<Net::NB>::BYTES;\n"
+          "  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(\n"
+          "      qcut_smem + (size_t)n_warps_cta * QcutStage<Net::NB>::BYTES) + warp;\n"
+          "  qcut_warp_stream<Net::NB, Net>(data, pubs, tiles, n_tiles, (int64_t)blockIdx.x * n_warps_cta + warp,\n"
+          "                                 (int64_t)gridDim.x * n_warps_cta, tallies, stage, mbar, lane, groups);\n"
+          "}\n";
+  } else {
+    os << "  const int lane = threadIdx.x & 31;\n"
+          "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+          "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
+          "       tile += n_warps) {\n"
+          "    const QcutTile te = tiles[tile];\n"
+          "    const QcutPub pub = pubs[te.pub];\n"
+          "    const int variant = (int)groups[pub.group].variant;\n"
+          "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+          "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+          "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Net::NB;\n"
+          "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "    uint32_t acc[Net::NACC];\n"
+          "    qcut_lane_tile_net<Net::NB, Net>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc, variant);\n"
+          "    Net::flush(acc, ns, lane, tallies + pub.tally_offset, variant);\n"
+          "  }\n"
+          "}\n";
+  }
+  os << "#endif\n";
+  return os.str();
+}
+
 // The translation unit for one group.  Pure host code.
 std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out,
                                    bool staged, int threads, int prefetch, bool allow_split, bool* split_out,
@@ -499,8 +571,8 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
           "  uint8_t* stage = qcut_smem + (size_t)warp * QcutStage<Terms::NB>::BYTES;\n"
           "  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(\n"
           "      qcut_smem + (size_t)n_warps_cta * QcutStage<Terms::NB>::BYTES) + warp;\n"
-          "  qcut_warp_stream<Terms::NB, Terms>(data, pubs, tiles, n_tiles, (int64_t)blockIdx.x * n_warps_cta + warp,\n"
-          "                                     (int64_t)gridDim.x * n_warps_cta, tallies, stage, mbar, lane);\n"
+          "  qcut_warp_stream<Terms::NB, QcutSingleNet<Terms> >(data, pubs, tiles, n_tiles, (int64_t)blockIdx.x * n_warps_cta + warp,\n"
+          "                                     (int64_t)gridDim.x * n_warps_cta, tallies, stage, mbar, lane, nullptr);\n"
           "}\n";
   } else {
     if (prefetch < 2) {
@@ -754,6 +826,19 @@ int jit_build(qcut_plan* plan, bool load) {
     if (plan->jit_cancel.load()) {  // the plan is being destroyed while its background compilation runs
       rcs[i] = QCUT_ERR_JIT;
       errors[i] = "cancelled";
+      return;
+    }
+    if (!jk.variants.empty() && jk.inline_switch) {
+      std::vector<const qcut_group_desc*> gds;
+      for (int g : jk.variants) gds.push_back(&plan->groups[g]);
+      jk.threads = 256;
+      jk.min_blocks = 2;
+      jk.nb_obs = (int)gds.front()->nb_obs;
+      // these kernels wait on memory (a few terms per group): staged stream unless switched off
+      const char* env_as = std::getenv("QCUT_JIT_AUTO_STAGED");
+      jk.staged = (plan->flags & QCUT_PLAN_STAGED) != 0 || !(env_as && *env_as && std::atoi(env_as) == 0);
+      jk.source = generate_switch_source(gds, plan->masks.data(), jk.threads, jk.min_blocks, jk.staged);
+      rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
       return;
     }
     if (!jk.variants.empty()) {

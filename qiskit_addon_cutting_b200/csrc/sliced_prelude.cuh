@@ -442,6 +442,23 @@ QCUT_DEV void qcut_lane_tile(const uint8_t* __restrict__ obs, const uint8_t* __r
   }
 }
 
+// Same loop for a kernel that serves many small groups: Net::run switches on the variant of the tile's group.
+template <int NB, class Net>
+QCUT_DEV void qcut_lane_tile_net(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns, int lane,
+                                 uint32_t* acc, int variant) {
+  typedef QcutGeo<NB> G;
+#pragma unroll
+  for (int r = 0; r < Net::NACC; ++r) acc[r] = 0;
+  for (int s0 = 0; s0 < ns; s0 += G::STEP_SHOTS) {
+    const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
+    uint32_t a[G::BLOCKS][32];
+    uint32_t qp[G::BATCHES];
+    qcut_step_any<NB>(obs + (uint64_t)s0 * NB, qpd + (uint64_t)s0 * nbq, nbq, n, lane, a, qp);
+#pragma unroll
+    for (int u = 0; u < G::BATCHES; ++u) Net::run(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], acc, variant);
+  }
+}
+
 // ---- term engine A', 8-byte rows, one 32x32 block at a time ("split") ----------------------------------
 // The all-at-once form above keeps both blocks of a step -- 64 bit-plane registers -- live through the whole XOR
 // network: with the packed counters that is 128 registers, 16 warps per SM, and the profile shows the warps
@@ -996,6 +1013,40 @@ QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long lo
     if (r < NACC && t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
   }
 }
+// The same flush for a network whose number of terms is only known at run time (kernels that serve many small
+// groups, Net::run switches on the group's variant): T terms in nacc = ceil(T / 4) <= MAXNACC <= 8 packed registers,
+// so every lane owns at most one (register, field).
+template <int MAXNACC>
+QCUT_DEV void qcut_flush_rt(const uint32_t* acc, int T, int nacc, int ns, int lane, unsigned long long* __restrict__ tally) {
+  const int field = lane & 3;
+  const bool odd_field = field & 1;
+  const uint32_t shift = (field & 2) ? 16u : 0u;
+  const int owner = lane >> 2;
+  uint32_t mine = 0;
+#pragma unroll
+  for (int r = 0; r < MAXNACC; ++r) {
+    const uint32_t ev = __reduce_add_sync(0xffffffffu, acc[r] & 0x00FF00FFu);
+    const uint32_t od = __reduce_add_sync(0xffffffffu, (acc[r] >> 8) & 0x00FF00FFu);
+    const uint32_t val = ((odd_field ? od : ev) >> shift) & 0xFFFFu;
+    if (r == owner) mine = val;
+  }
+  const int t = field * nacc + owner;
+  if (owner < nacc && t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine));
+}
+
+// What the tile loops need to know about the term network(s) of a kernel.  One group per kernel: the generated
+// `struct Terms`; many small groups per kernel: a generated `struct Net` whose run() switches on the variant index of
+// the tile's group (QcutGroup::variant).
+template <class Terms>
+struct QcutSingleNet {
+  static const int NB = Terms::NB;
+  static const int NACC = Terms::NACC;
+  static const bool MULTI = false;
+  static QCUT_MDEV void run(const uint32_t* P, const uint32_t* Q, uint32_t qp, uint32_t* acc, int) { Terms::run(P, Q, qp, acc); }
+  static QCUT_MDEV void flush(const uint32_t* acc, int ns, int lane, unsigned long long* tally, int) {
+    qcut_flush<Terms::T>(acc, ns, lane, tally);
+  }
+};
 #endif  // !QCUT_HOST_EMU
 #if !defined(QCUT_HOST_EMU) && defined(QCUT_WITH_VARIANTS)
 // (experiments that measured slower than the default, DESIGN.md section 4: the generator defines QCUT_WITH_VARIANTS
@@ -1091,11 +1142,11 @@ QCUT_DEV void qcut_stage_issue(uint32_t buf, uint32_t mbar, const uint8_t* obs_s
   if (qb) qcut_bulk_g2s(buf + QcutStage<NB>::OBS_BYTES, qpd_s, qb, mbar);
 }
 
-template <int NB, class Terms>
+template <int NB, class Net>
 QCUT_DEV void qcut_warp_stream(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,
                                const QcutTile* __restrict__ tiles, const int64_t n_tiles, int64_t first_tile,
                                int64_t tile_stride, unsigned long long* __restrict__ tallies, uint8_t* stage,
-                               unsigned long long* mbar_ptr, int lane) {
+                               unsigned long long* mbar_ptr, int lane, const QcutGroup* __restrict__ groups) {
   typedef QcutGeo<NB> G;
   if (first_tile >= n_tiles) return;
   const uint32_t buf = qcut_smem_addr(stage);
@@ -1112,6 +1163,11 @@ QCUT_DEV void qcut_warp_stream(const uint8_t* __restrict__ data, const QcutPub* 
   QcutPub pub_next = pub;
   bool have_next = tile + tile_stride < n_tiles;
   if (have_next) { te_next = tiles[tile + tile_stride]; pub_next = pubs[te_next.pub]; }
+  int variant = 0, variant_next = 0;  // which network of a multi-group kernel serves the tile
+  if (Net::MULTI) {
+    variant = (int)groups[pub.group].variant;
+    if (have_next) variant_next = (int)groups[pub_next.group].variant;
+  }
 
   int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;
   int ns = (int)(((int64_t)pub.shots - shot0 < QCUT_TILE_SHOTS) ? (int64_t)pub.shots - shot0 : QCUT_TILE_SHOTS);
@@ -1122,9 +1178,9 @@ QCUT_DEV void qcut_warp_stream(const uint8_t* __restrict__ data, const QcutPub* 
   uint32_t parity = 0;
   if (lane == 0) qcut_stage_issue<NB>(buf, mbar, obs, qpd, nbq, ns < G::STEP_SHOTS ? ns : G::STEP_SHOTS);
 
-  uint32_t acc[Terms::NACC];
+  uint32_t acc[Net::NACC];
 #pragma unroll
-  for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+  for (int r = 0; r < Net::NACC; ++r) acc[r] = 0;
 
   for (;;) {
     const int n = (ns - s0 < G::STEP_SHOTS) ? ns - s0 : G::STEP_SHOTS;
@@ -1184,20 +1240,21 @@ QCUT_DEV void qcut_warp_stream(const uint8_t* __restrict__ data, const QcutPub* 
     if (n != G::STEP_SHOTS) qcut_mask_tail<NB>(n, lane, a, qp);
 #pragma unroll
     for (int u = 0; u < G::BATCHES; ++u)
-      Terms::run(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], acc);
+      Net::run(&a[0][u * G::PLANES], &a[G::BLOCKS - 1][0], qp[u], acc, variant);
 
     if (!last_step) {
       s0 += G::STEP_SHOTS;
       continue;
     }
     // ---- end of tile: flush, advance ----
-    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);
+    Net::flush(acc, ns, lane, tallies + pub.tally_offset, variant);
 #pragma unroll
-    for (int r = 0; r < Terms::NACC; ++r) acc[r] = 0;
+    for (int r = 0; r < Net::NACC; ++r) acc[r] = 0;
     if (!have_next) break;
     tile += tile_stride;
     te = te_next;
     pub = pub_next;
+    variant = variant_next;
     shot0 = n_shot0;
     ns = n_ns;
     nbq = n_nbq;
@@ -1205,7 +1262,11 @@ QCUT_DEV void qcut_warp_stream(const uint8_t* __restrict__ data, const QcutPub* 
     qpd = n_qpd;
     s0 = 0;
     have_next = tile + tile_stride < n_tiles;
-    if (have_next) { te_next = tiles[tile + tile_stride]; pub_next = pubs[te_next.pub]; }
+    if (have_next) {
+      te_next = tiles[tile + tile_stride];
+      pub_next = pubs[te_next.pub];
+      if (Net::MULTI) variant_next = (int)groups[pub_next.group].variant;
+    }
   }
 }
 #endif

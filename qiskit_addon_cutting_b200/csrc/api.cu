@@ -58,9 +58,10 @@ int launch_quasi(const qcut_pub_desc*, int64_t, const qcut_group_desc*, const ui
                  const uint64_t*, int, const uint64_t*, int, const double*, double*, cudaStream_t);
 int launch_recombine(const double*, bool, const uint32_t*, const uint32_t*, const double*, int, double*, cudaStream_t);
 
-// Groups with at least this many terms are worth an NVRTC specialisation: below it the (shared)
-// load + transposition cost dominates and the run-time-mask kernel is within a few percent.
-constexpr uint32_t kJitMinTerms = 12;
+// Groups with at least this many terms get an NVRTC-specialised kernel of their own; smaller groups share kernels
+// (their networks are a few instructions: what matters for them is the number and length of the launches -- cfg3
+// "local", 12 groups of ~9 terms on 1-7-byte rows, 2.45 GB: nine launches 0.785 of the copy peak, one launch 0.86).
+constexpr uint32_t kJitMinTerms = 33;
 // Multi-group kernels: distinct mask sets per kernel, and how many such kernels a plan may have
 // (groups beyond that use the run-time-mask kernel).
 constexpr size_t kMultiVariants = 24;
@@ -81,10 +82,13 @@ static void assign_jit_kernels(qcut_plan* plan) {
   // Pick the groups to specialise: the QCUT_MAX_JIT_KERNELS distinct (width, masks) sets with the
   // most terms among those with >= kJitMinTerms terms.
   {
+    uint32_t min_terms = kJitMinTerms;
+    if (const char* env_mt = std::getenv("QCUT_JIT_MIN_TERMS"))  // experiments
+      if (*env_mt && std::atoi(env_mt) > 0) min_terms = (uint32_t)std::atoi(env_mt);
     std::map<std::string, std::vector<int>> by_masks;
     for (int g = 0; g < n_groups; ++g) {
       const qcut_group_desc& gd = h_groups[g];
-      if (!jit_supports(gd) || (gd.n_terms < kJitMinTerms && gd.nb_obs <= 8)) continue;
+      if (!jit_supports(gd) || (gd.n_terms < min_terms && gd.nb_obs <= 8)) continue;
       std::string key(reinterpret_cast<const char*>(&gd.nb_obs), sizeof(gd.nb_obs));
       key.append(reinterpret_cast<const char*>(h_masks + gd.mask_offset), (size_t)gd.n_terms * gd.nb_obs);
       by_masks[key].push_back(g);
@@ -131,7 +135,7 @@ static void assign_jit_kernels(qcut_plan* plan) {
       }
       for (const auto& kv : by_width) {
         const auto& sets_w = kv.second;
-        if (sets_w.size() < kSwitchMinSets) {  // a handful of sets of this width: not worth a kernel of their own
+        if (sets_w.size() < kSwitchMinSets && by_width.size() > 1) {  // a handful of sets of this width among others
           rest.insert(rest.end(), sets_w.begin(), sets_w.end());
           continue;
         }

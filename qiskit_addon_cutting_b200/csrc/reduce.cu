@@ -219,18 +219,31 @@ reduce_partial_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* _
 // consecutive tuples and every lane keeps its running sum in a register (ascending i inside the
 // chunk).  No shared memory; the descriptor -> tally load chains of B tuples x L subsystems are in
 // flight together per lane and up to 64 warps per SM hide the rest of the latency.
+// Measured on cfg4 (97 000 tuples x 271 observables, step minus K1): 8 tuples in flight per lane at 114 registers
+// 0.161 ms; 4 tuples under a 64-register cap (8 CTAs of 4 warps per SM) 0.134 ms; 2 tuples at 42 registers 0.143 ms.
+// The kernel waits on its descriptor -> tally load chains and on fp64 divisions: resident warps hide more of that
+// than loads in flight per lane.  (64 tuples per warp keeps the summation order, hence every bit of the result.)
+#ifndef QCUT_K2_B       // tuples whose load chains a lane keeps in flight (experiments: -DQCUT_K2_B=..)
+#define QCUT_K2_B 4
+#endif
+#ifndef QCUT_K2_MINB    // CTAs per SM the stream kernel is compiled for (register cap)
+#define QCUT_K2_MINB 8
+#endif
+#ifndef QCUT_K2_SUB
+#define QCUT_K2_SUB 64
+#endif
 constexpr int kStreamWarps = 4;
-constexpr int kStreamSub = 64;                              // tuples per warp
+constexpr int kStreamSub = QCUT_K2_SUB;                     // tuples per warp
 constexpr int kStreamChunk = kStreamWarps * kStreamSub;    // tuples per CTA = one partial sum
 
 template <typename TallyT, int L>
-__global__ void __launch_bounds__(kStreamWarps * 32)
+__global__ void __launch_bounds__(kStreamWarps * 32, (L == 1 || L == 2) ? QCUT_K2_MINB : 4)  // (3-4 subsystems spill under 64 registers)
 reduce_stream_kernel(const TallyT* __restrict__ tallies, const qcut_pub_desc* __restrict__ pubs,
                      const qcut_label_desc* __restrict__ labels, int n_labels,
                      const uint32_t* __restrict__ lookup_start, const qcut_slot* __restrict__ lookup,
                      const double* __restrict__ coeffs, int64_t n_coeffs, int n_obs, int64_t n_chunks,
                      double* __restrict__ partial) {
-  constexpr int B = (L <= 2) ? 8 : 4;
+  constexpr int B = (L <= 2) ? QCUT_K2_B : (QCUT_K2_B < 4 ? QCUT_K2_B : 4);
   __shared__ double s_sub[kStreamWarps][32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;

@@ -59,6 +59,7 @@ struct JitKernel {
   bool split = false;  // 8-byte rows processed one 32x32 block at a time (block 1 parked in shared memory)
   bool pipe = false;   // loads of the next step issued from inside the term network (qcut_warp_pipe)
   bool inline_switch = false;  // multi-group kernel of one row width: the groups' networks behind a switch (jit.cu)
+  bool slab = false;   // rows of 16 / 24 / 32 bytes processed in 8-byte slabs (qcut_lane_tile_slab)
   bool sacc = false;   // packed counters in shared memory (qcut_lane_tile_sacc)
   int smem_bytes = 0;
 };

@@ -118,7 +118,7 @@ struct TermEmitter {
 
 // Returns true when the split form (run0 / run1) was emitted.
 static bool emit_terms(std::ostringstream& os, const std::string& name, const qcut_group_desc& gd, const uint8_t* masks,
-                       bool* pipe_out = nullptr, bool* sacc_out = nullptr, bool* il_out = nullptr) {
+                       bool* pipe_out = nullptr, bool* sacc_out = nullptr, bool* il_out = nullptr, bool* slab_out = nullptr) {
   const uint32_t T = gd.n_terms, nb = gd.nb_obs, nacc = (T + 3) / 4;
   TermEmitter em{os, gd, masks, T, nb, nacc};
   std::vector<uint32_t> all(T);
@@ -294,6 +294,74 @@ static bool emit_terms(std::ostringstream& os, const std::string& name, const qc
       os << "  }\n";
     }
   }
+  // Rows of 16 / 24 / 32 bytes, sparse masks: the row is processed in 8-byte slabs (qcut_lane_tile_slab), counters in
+  // shared memory.  A term that lives in one slab is evaluated in that slab's pass; a term that straddles slabs starts a
+  // partial word K[i] in the first slab it touches and is counted in the last.  Packed counter r = t % NACC, field
+  // t / NACC as everywhere; a pass loads / stores only the counter groups it adds to.
+  bool slab = false;
+  if (slab_out && (nb == 16 || nb == 24 || nb == 32)) {
+    const uint32_t n_slabs = nb / 8;
+    size_t lop3 = 0;
+    std::vector<uint32_t> first(T, n_slabs), last(T, 0);
+    std::vector<int> kslot(T, -1);
+    int nk = 0;
+    for (uint32_t t = 0; t < T; ++t) {
+      lop3 += (size_t)(em.weight(t, 0, nb) + 1) / 2;
+      for (uint32_t sl = 0; sl < n_slabs; ++sl)
+        if (em.weight(t, 8 * sl, 8 * sl + 8) > 0) { first[t] = std::min(first[t], sl); last[t] = sl; }
+      if (first[t] == n_slabs) first[t] = last[t] = 0;  // identity: counted with slab 0
+      if (first[t] != last[t]) kslot[t] = nk++;
+    }
+    slab = lop3 <= (size_t)T * 2 + (size_t)nk && nk <= 16;
+    if (slab) {
+      os << "  static const int NK = " << nk << ";\n";
+      os << "  template <int SLAB>\n"
+            "  static QCUT_MDEV void run_slab(const uint32_t* __restrict__ P, const uint32_t* __restrict__ Q, const uint32_t qp,\n"
+            "                                 const QcutSacc S, uint32_t* __restrict__ K) {\n"
+            "    (void)P; (void)Q; (void)K;\n    uint32_t x;\n    qcut_u4 q;\n";
+      static const char* const word[4] = {"q.x", "q.y", "q.z", "q.w"};
+      auto planes_of = [&](uint32_t t, uint32_t sl) {
+        std::string e;
+        for (uint32_t byte = 8 * sl; byte < 8 * sl + 8; ++byte)
+          for (uint32_t bit = 0; bit < 8; ++bit)
+            if ((em.row(t)[byte] >> bit) & 1u)
+              e += std::string(" ^ ") + ((byte % 8) >= 4 ? "Q[" : "P[") + std::to_string(8 * (byte % 4) + bit) + "]";
+        return e;
+      };
+      for (uint32_t sl = 0; sl < n_slabs; ++sl) {
+        os << "    " << (sl ? "else " : "") << "if constexpr (SLAB == " << sl << ") {\n";
+        // partial words of the straddling terms that pass through this slab without ending here
+        for (uint32_t t = 0; t < T; ++t)
+          if (kslot[t] >= 0 && sl >= first[t] && sl < last[t] && (sl == first[t] || em.weight(t, 8 * sl, 8 * sl + 8) > 0))
+            os << "      K[" << kslot[t] << "] = " << (sl == first[t] ? "qp" : "K[" + std::to_string(kslot[t]) + "]")
+               << planes_of(t, sl) << ";\n";
+        for (uint32_t g = 0; 4 * g < nacc; ++g) {
+          bool any = false;
+          for (uint32_t f = 0; f < 4 && !any; ++f)
+            for (uint32_t j = 0; j < 4 && !any; ++j) {
+              const uint32_t r = 4 * g + j, t = f * nacc + r;
+              any = r < nacc && t < T && last[t] == sl;
+            }
+          if (!any) continue;
+          os << "      q = S.ld4(" << g << ");\n";
+          for (uint32_t f = 0; f < 4; ++f)
+            for (uint32_t j = 0; j < 4; ++j) {
+              const uint32_t r = 4 * g + j, t = f * nacc + r;
+              if (r >= nacc || t >= T || last[t] != sl) continue;
+              os << "      x = " << (kslot[t] >= 0 ? "K[" + std::to_string(kslot[t]) + "]" : std::string("qp")) << planes_of(t, sl)
+                 << ";\n      " << word[j] << " += (uint32_t)__popc(x)";
+              if (f) os << " << " << 8 * f;
+              os << ";\n";
+            }
+          os << "      S.st4(" << g << ", q);\n";
+        }
+        os << "    }\n";
+      }
+      os << "  }\n";
+    }
+  }
+  os << "  static const int SLAB = " << (slab ? 1 : 0) << ";\n";
+  if (slab_out) *slab_out = slab;
   os << "  static const int IL = " << (il ? 1 : 0) << ";\n";
   if (il_out) *il_out = il;
   os << "  static const int SACC = " << (sacc ? 1 : 0) << ";\n";
@@ -421,7 +489,7 @@ std::string generate_switch_source(const std::vector<const qcut_group_desc*>& gd
 // The translation unit for one group.  Pure host code.
 std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* masks, int* min_blocks_out,
                                    bool staged, int threads, int prefetch, bool allow_split, bool* split_out,
-                                   bool allow_pipe, bool* pipe_out, bool allow_sacc, bool* sacc_out) {
+                                   bool allow_pipe, bool* pipe_out, bool allow_sacc, bool* sacc_out, bool* slab_out) {
   if (!jit_supports(gd)) return std::string();
   const uint32_t T = gd.n_terms, nb = gd.nb_obs;
   std::ostringstream terms;
@@ -431,9 +499,15 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   const bool want_il = plain && env_il && *env_il && std::atoi(env_il) != 0;
   const bool want_pipe = allow_pipe && plain && !allow_sacc && !want_il;
   const bool want_sacc = allow_sacc && plain && !want_il;
+  // rows of 16 / 24 / 32 bytes with sparse masks: 8-byte slabs on the narrow-row engine (QCUT_JIT_SLAB=0: the
+  // shared-memory wide-row engine for these widths too)
+  const char* env_slab = std::getenv("QCUT_JIT_SLAB");
+  const bool want_slab = !(env_slab && *env_slab && std::atoi(env_slab) == 0);
+  bool slab = false;
   const bool split = emit_terms(terms, "Terms", gd, masks, want_pipe ? &pipe : nullptr, want_sacc ? &sacc : nullptr,
-                                want_il ? &il : nullptr) &&
+                                want_il ? &il : nullptr, want_slab ? &slab : nullptr) &&
                      allow_split && !staged && prefetch == 0;
+  if (slab_out) *slab_out = slab;
   if (split_out) *split_out = split;
   if (pipe_out) *pipe_out = pipe;
   if (sacc_out) *sacc_out = sacc;
@@ -459,6 +533,49 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   os << "#define QCUT_SACC_STRIDE " << 16 * threads << "\n";
   os << kPrelude << "\n";
   os << terms.str();
+  if (slab) {
+    os << "#ifndef QCUT_HOST_EMU\n"
+          "extern \"C\" __global__ void __launch_bounds__(" << threads << ", 2)\n"
+          "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  extern __shared__ __align__(16) uint32_t qcut_smem[];\n"
+          "  const int lane = threadIdx.x & 31;\n"
+          "  const QcutSacc S = {(uint32_t)__cvta_generic_to_shared(qcut_smem) + 16u * threadIdx.x};\n"
+          "  qcut_sacc_clear<Terms::NACC>(S);\n"
+          "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+          "  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles;\n"
+          "       tile += n_warps) {\n"
+          "    const QcutTile te = tiles[tile];\n"
+          "    const QcutPub pub = pubs[te.pub];\n"
+          "    const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "    const int64_t left = (int64_t)pub.shots - shot0;\n"
+          "    const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+          "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
+          "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "    qcut_lane_tile_slab<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, S);\n"
+          "    uint32_t acc[Terms::NACC];\n"
+          "    qcut_sacc_take<Terms::NACC>(S, acc);\n"
+          "    qcut_flush<Terms::T>(acc, ns, lane, tallies + pub.tally_offset);\n"
+          "  }\n"
+          "}\n"
+          "#else\n"
+          "extern \"C\" int qcut_emu_lane_tile(const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
+          "                                  uint32_t* odd_out) {\n"
+          "  static uint32_t column[4 * ((Terms::NACC + 3) / 4)];\n"
+          "  const QcutSacc S = {column};\n"
+          "  qcut_sacc_clear<Terms::NACC>(S);\n"
+          "  qcut_lane_tile_slab<Terms::NB, Terms>(obs, qpd, nbq, ns, lane, S);\n"
+          "  uint32_t acc[Terms::NACC];\n"
+          "  qcut_sacc_take<Terms::NACC>(S, acc);\n"
+          "  for (int t = 0; t < Terms::T; ++t) odd_out[t] = (acc[t % Terms::NACC] >> (8 * (t / Terms::NACC))) & 0xFFu;\n"
+          "  return Terms::T;\n"
+          "}\n"
+          "extern \"C\" int qcut_emu_rt_lane_tile(int, const uint8_t*, const uint8_t*, int, int, int, const uint32_t*, int, int,\n"
+          "                                     uint32_t*) { return -1; }\n"
+          "#endif\n";
+    return os.str();
+  }
   if (nb > 8) {
     // Wide rows: 4 warps per CTA (2 for rows of more than 16 bytes), per-warp raw + plane buffers in dynamic
     // shared memory.
@@ -890,7 +1007,7 @@ int jit_build(qcut_plan* plan, bool load) {
     const char* env_sacc = std::getenv("QCUT_JIT_SACC");
     const bool allow_sacc = env_sacc && *env_sacc && std::atoi(env_sacc) != 0;
     jk.source = generate_sliced_source(plan->groups[jk.group], plan->masks.data(), &jk.min_blocks, jk.staged, jk.threads, prefetch,
-                                       allow_split, &jk.split, allow_pipe, &jk.pipe, allow_sacc, &jk.sacc);
+                                       allow_split, &jk.split, allow_pipe, &jk.pipe, allow_sacc, &jk.sacc, &jk.slab);
     rcs[i] = compile_sliced_source(jk.source, &jk.cubin, &jk.log, &errors[i]);
   };
   std::atomic<size_t> next{0};
@@ -922,7 +1039,13 @@ int jit_build(qcut_plan* plan, bool load) {
     }
     if (err == cudaSuccess) err = cudaLibraryGetKernel(&jk.kernel, jk.library, "qcut_tally_sliced");
     if (err != cudaSuccess) return cuda_fail(err, "cudaLibraryLoadData(qcut_tally_sliced)");
-    if (jk.variants.empty() && jk.nb_obs > 8) {
+    if (jk.variants.empty() && jk.slab) {
+      // 8-byte slabs of a 16 / 24 / 32-byte row: 256 threads, 2 CTAs per SM, packed counters in shared memory
+      jk.smem_bytes = 16 * jk.threads * (int)(((plan->groups[jk.group].n_terms + 3) / 4 + 3) / 4);
+      int dev = 0;
+      QCUT_CUDA(cudaGetDevice(&dev));
+      QCUT_CUDA(cudaKernelSetAttributeForDevice(jk.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, jk.smem_bytes, dev));
+    } else if (jk.variants.empty() && jk.nb_obs > 8) {
       // wide rows: 4 (2 above 16 bytes) warps per CTA, per warp raw buffer (32 lanes x (4 NB + 1) words) + row /
       // plane store -- QcutWide<NB> in sliced_prelude.cuh
       const int blocks = (jk.nb_obs + 3) / 4;
@@ -1002,7 +1125,7 @@ size_t qcut_generate_source(const qcut_group_desc* h_groups, int n_groups, const
   const std::string src = qcut::generate_sliced_source(gd, h_masks, nullptr, false, 256, 0,
                                                        env_split && *env_split && std::atoi(env_split) != 0, nullptr,
                                                        env_pipe && *env_pipe && std::atoi(env_pipe) != 0, nullptr,
-                                                       env_sacc && *env_sacc && std::atoi(env_sacc) != 0, nullptr);
+                                                       env_sacc && *env_sacc && std::atoi(env_sacc) != 0, nullptr, nullptr);
   if (src.empty()) return 0;
   if (buf && buf_len) {
     const size_t n = src.size() < buf_len - 1 ? src.size() : buf_len - 1;

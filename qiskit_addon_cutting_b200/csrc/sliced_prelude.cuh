@@ -958,6 +958,101 @@ QCUT_DEV void qcut_lane_tile_wide(const uint8_t* __restrict__ obs, const uint8_t
   }
 }
 
+// ---- wide rows in 8-byte slabs (NB = 16, 24, 32): the narrow-row engine on one slab of the row at a time ("slab") ----
+// The wide-row engine above parks up to 256 bit-planes in shared memory and runs at 8 warps per SM (0.35 of the copy
+// peak on 16-byte rows).  A local observable on an un-partitioned 127-qubit register touches one 64-bit slab of the row
+// per term, a handful of terms two; so a step of 1024 shots is processed slab by slab: 32 eight-byte loads per lane
+// (shot 32 k + lane -> row k of the slab's two 32x32 blocks; the second slab re-reads the sectors of the first from
+// L2), two in-register transpositions, the slab's terms on registers -- packed counters in shared memory (QcutSacc),
+// the partial parity words of the cross-slab terms in K[] registers.  The qpd parity plane is built once per step from
+// eight coalesced 4-byte loads per lane and four shuffles that bring every lane the bits of ITS shots.
+#ifndef QCUT_HOST_EMU
+QCUT_DEV void qcut_ld8(const uint8_t* p, uint32_t& lo, uint32_t& hi) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+#else
+QCUT_DEV void qcut_ld8(const uint8_t* p, uint32_t& lo, uint32_t& hi) { memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4); }
+#endif
+
+template <int NB, bool FULL>
+QCUT_DEV void qcut_slab_loads(const uint8_t* __restrict__ obs_s, int slab, int n, int lane, uint32_t (*a)[32]) {
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    a[0][k] = 0;
+    a[1][k] = 0;
+    if (FULL || 32 * k + lane < n) qcut_ld8(obs_s + (uint64_t)(32 * k + lane) * NB + 8 * slab, a[0][k], a[1][k]);
+  }
+}
+
+// bit k of the result = parity of ALL bits of the qpd row of shot 32 k + lane (0 for shots >= n)
+template <bool FULL>
+QCUT_DEV uint32_t qcut_slab_qpd(const uint8_t* __restrict__ qpd_s, int nbq, int n, int lane) {
+#ifndef QCUT_HOST_EMU
+  if (nbq == 1) {
+    uint32_t w = 0;  // bit 4 j + b = parity of the qpd byte of shot 128 j + 4 lane + b
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t v = 0;
+      if (FULL || 128 * j + 4 * lane < n) v = qcut_ld4(qpd_s + 128 * j + 4 * lane);
+      w |= ((qcut_byte_parity(v) * 0x01020408u) >> 24) << (4 * j);
+    }
+    // shot 32 k + L with k = 4 j + m sits in lane (L >> 2) + 8 m at bit 4 j + (L & 3)
+    const int b = lane & 3;
+    uint32_t qp = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) qp |= ((__shfl_sync(0xffffffffu, w, (lane >> 2) + 8 * m) >> b) & 0x11111111u) << m;
+    return qp;  // (shots >= n: the caller masks them)
+  }
+#endif
+  uint32_t qp = 0;
+  for (int k = 0; k < 32; ++k) {
+    const int shot = 32 * k + lane;
+    if (shot < n) {
+      uint32_t x = 0;
+      for (int bb = 0; bb < nbq; ++bb) x ^= qcut_ld1(qpd_s + (uint64_t)shot * nbq + bb);
+      qp |= (uint32_t)(__popc(x) & 1) << k;
+    }
+  }
+  return qp;
+}
+
+template <int NB, class Terms, int SLAB, bool FULL>
+QCUT_DEV void qcut_slab_pass(const uint8_t* __restrict__ obs_s, int n, int lane, uint32_t qp, uint32_t valid, const QcutSacc S,
+                             uint32_t* K) {
+  uint32_t a[2][32];
+  qcut_slab_loads<NB, FULL>(obs_s, SLAB, n, lane, a);
+  qcut_transpose32(a[0]);
+  qcut_transpose32(a[1]);
+  if (!FULL) {  // rows past the end of the PUB were loaded as zero; drop their shots from the term words through qp / valid
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { a[0][i] &= valid; a[1][i] &= valid; }
+  }
+  Terms::template run_slab<SLAB>(a[0], a[1], qp, S, K);
+  if constexpr (SLAB + 1 < NB / 8) qcut_slab_pass<NB, Terms, SLAB + 1, FULL>(obs_s, n, lane, qp, valid, S, K);
+}
+
+// counters in S (cleared on entry by the previous qcut_sacc_take / qcut_sacc_clear)
+template <int NB, class Terms>
+QCUT_DEV void qcut_lane_tile_slab(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns, int lane,
+                                  const QcutSacc S) {
+  for (int s0 = 0; s0 < ns; s0 += 1024) {
+    const int n = (ns - s0 < 1024) ? ns - s0 : 1024;
+    const uint8_t* __restrict__ obs_s = obs + (uint64_t)s0 * NB;
+    const uint8_t* __restrict__ qpd_s = qpd + (uint64_t)s0 * nbq;
+    uint32_t K[Terms::NK > 0 ? Terms::NK : 1];
+    if (n == 1024) {
+      const uint32_t qp = qcut_slab_qpd<true>(qpd_s, nbq, n, lane);
+      qcut_slab_pass<NB, Terms, 0, true>(obs_s, n, lane, qp, 0xFFFFFFFFu, S, K);
+    } else {
+      uint32_t valid = 0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) valid |= (uint32_t)(32 * k + lane < n) << k;
+      const uint32_t qp = qcut_slab_qpd<false>(qpd_s, nbq, n, lane) & valid;
+      qcut_slab_pass<NB, Terms, 0, false>(obs_s, n, lane, qp, valid, S, K);
+    }
+  }
+}
+
 // ---- term engine B: run-time masks, bit-planes parked in shared memory -------------------------
 // planes[p * 32] is this lane's word of memory-bit plane p (the caller passes the lane's column).
 // mask words are the little-endian words of the mask row in memory order (plan table).

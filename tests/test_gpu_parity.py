@@ -140,6 +140,33 @@ def test_staged_stream_of_steps_matches_direct_loads(lib, monkeypatch, nbits, n_
         assert ("qcut_warp_stream" in source.split('extern "C"', 1)[1]) == staged
 
 
+@pytest.mark.parametrize("nbits", [127, 190, 256])
+def test_slab_engine_for_16_24_32_byte_rows(lib, monkeypatch, nbits):
+    """Local observable on a 127- / 190- / 256-bit register (16 / 24 / 32-byte rows): processed in 8-byte slabs on the
+    narrow-row engine, bit-exact against the oracle and against the shared-memory wide-row engine (QCUT_JIT_SLAB=0)."""
+    step = 2 if nbits <= 128 else 3
+    labels = ["".join("Z" if nbits - 1 - i == q else "I" for i in range(nbits)) for q in range(nbits)]
+    bonds = [(q, q + 1) for q in range(0, nbits - 1, step)] + [(60, 70), (63, 64), (5, 126), (100, nbits - 1)]
+    if nbits > 128:
+        bonds += [(120, 135), (10, 70, 150)]
+    labels += ["".join("Z" if nbits - 1 - i in qs else "I" for i in range(nbits)) for qs in bonds]
+    labels.append("I" * nbits)
+    observables = {"A": PauliList(labels)}
+    pubs = []
+    for i, shots in enumerate([9000, 1, 4096, 0, 12289, 1024, 5000, 3071]):
+        one = _cases.make_results(observables, 1, shots, 1 + 8 * (i % 4 == 3), seed=nbits * 100 + i)
+        pubs.append(one["A"][0])
+    results = {"A": PrimitiveResult(pubs)}
+    coefficients = [(1.0, WeightType.EXACT)] * len(pubs)
+    batch, got, want = _device_tallies(results, coefficients, observables)
+    assert np.array_equal(got, want)
+    assert "qcut_lane_tile_slab" in batch.plan.source(_lib.KERNEL_JIT0).split('extern "C"', 1)[1]
+    monkeypatch.setenv("QCUT_JIT_SLAB", "0")
+    batch2, got2, _ = _device_tallies(results, coefficients, observables, _lib.PLAN_STAGED)  # (other flags: not the cached plan)
+    assert np.array_equal(got2, want)
+    assert "qcut_lane_tile_wide" in batch2.plan.source(_lib.KERNEL_JIT0).split('extern "C"', 1)[1]
+
+
 def test_rows_of_17_to_32_bytes_use_the_specialised_kernel(lib):
     """A 156-qubit register (20-byte rows) is handled by the wide-row engine, 33-byte rows by the generic kernel."""
     for nbits, specialised in ((156, True), (256, True), (264, False)):

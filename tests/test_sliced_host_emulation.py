@@ -232,3 +232,27 @@ def test_emulated_interleaved_engine_for_8_byte_rows(lib, monkeypatch, shots):
         assert "IL = 1" in source and "qcut_lane_tile_il<Terms>" in source.split("extern \"C\"", 1)[1]
         got, covered = _host_emu.emulate_tallies(tables, data, "jit")
         assert covered.all() and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("nbits", [127, 128, 190, 256])
+@pytest.mark.parametrize("shots", [1, 1024, 1500, 4100])
+def test_emulated_slab_engine_for_16_24_32_byte_rows(lib, nbits, shots):
+    """Rows of 16 / 24 / 32 bytes with a local observable (what an un-partitioned 127-qubit register looks like): the row is
+    processed in 8-byte slabs on the narrow-row engine (qcut_lane_tile_slab) -- slab-local terms, terms that straddle two
+    or three slabs (partial words kept between the passes), identity, ragged tails, 1- and 2-byte qpd rows."""
+    labels = ["".join("Z" if nbits - 1 - i == q else "I" for i in range(nbits)) for q in range(nbits)]
+    bonds = [(q, q + 1) for q in range(0, nbits - 1, 2 if nbits <= 128 else 3)] + [(60, 70), (63, 64), (5, 126), (100, nbits - 1)]
+    if nbits > 128:
+        bonds += [(120, 135), (10, 70, 150)]
+    labels += ["".join("Z" if nbits - 1 - i in qs else "I" for i in range(nbits)) for qs in bonds]
+    labels.append("I" * nbits)
+    observables = {"A": PauliList(labels)}
+    for qbits in (3, 11):
+        results = _cases.make_results(observables, 1, shots, qbits, seed=shots + qbits + nbits)
+        tables, data, want = _stage_host(results, [(1.0, WeightType.EXACT)], observables)
+        source = _lib.generate_source(tables.groups, tables.masks, 0)
+        assert "SLAB = 1" in source and "qcut_lane_tile_slab<Terms::NB, Terms>" in source.split("extern \"C\"", 1)[1]
+        mm, guarded = _guarded_copy(data, tables.data_bytes)
+        got, covered = _host_emu.emulate_tallies(tables, guarded, "jit")
+        assert covered.all() and np.array_equal(got, want)
+        del guarded

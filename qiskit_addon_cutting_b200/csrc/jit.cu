@@ -531,6 +531,10 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
     os << "#define QCUT_SPLIT_PHASES " << (phases == 2 || phases == 4 ? phases : 1) << "\n";
   }
   os << "#define QCUT_SACC_STRIDE " << 16 * threads << "\n";
+  if (slab) {
+    const char* env_pf = std::getenv("QCUT_JIT_SLAB_PREFETCH");
+    if (!(env_pf && *env_pf && std::atoi(env_pf) == 0)) os << "#define QCUT_SLAB_PREFETCH 1\n";
+  }
   os << kPrelude << "\n";
   os << terms.str();
   if (slab) {

@@ -1031,6 +1031,14 @@ QCUT_DEV void qcut_slab_pass(const uint8_t* __restrict__ obs_s, int n, int lane,
   if constexpr (SLAB + 1 < NB / 8) qcut_slab_pass<NB, Terms, SLAB + 1, FULL>(obs_s, n, lane, qp, valid, S, K);
 }
 
+// The kernel waits on its loads (ncu: long_scoreboard on top, issue slots 37 % busy): while a step is processed the copy
+// engine pulls the rows of the next step of the tile into L2 (no registers, no shared memory, two instructions).
+QCUT_DEV void qcut_slab_prefetch_l2(const uint8_t* p, uint32_t bytes) {
+#ifndef QCUT_HOST_EMU
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+#endif
+}
+
 // counters in S (cleared on entry by the previous qcut_sacc_take / qcut_sacc_clear)
 template <int NB, class Terms>
 QCUT_DEV void qcut_lane_tile_slab(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ qpd, int nbq, int ns, int lane,
@@ -1040,6 +1048,13 @@ QCUT_DEV void qcut_lane_tile_slab(const uint8_t* __restrict__ obs, const uint8_t
     const uint8_t* __restrict__ obs_s = obs + (uint64_t)s0 * NB;
     const uint8_t* __restrict__ qpd_s = qpd + (uint64_t)s0 * nbq;
     uint32_t K[Terms::NK > 0 ? Terms::NK : 1];
+#ifdef QCUT_SLAB_PREFETCH
+    if (lane == 0 && ns - s0 > 1024) {
+      const int rest = ns - s0 - 1024 < 1024 ? ns - s0 - 1024 : 1024;
+      qcut_slab_prefetch_l2(obs_s + 1024 * NB, ((uint32_t)rest * NB + 15u) & ~15u);
+      qcut_slab_prefetch_l2(qpd_s + 1024 * nbq, ((uint32_t)rest * (uint32_t)nbq + 15u) & ~15u);
+    }
+#endif
     if (n == 1024) {
       const uint32_t qp = qcut_slab_qpd<true>(qpd_s, nbq, n, lane);
       qcut_slab_pass<NB, Terms, 0, true>(obs_s, n, lane, qp, 0xFFFFFFFFu, S, K);

@@ -1123,6 +1123,42 @@ QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long lo
     if (r < NACC && t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
   }
 }
+// The flush in two halves, for kernels in which a warp takes the tiles of a PUB two at a time (8192 shots): the warp
+// sums of each tile are gathered into the owner lanes' registers (the 8-bit per-lane fields hold one tile), and ONE
+// update per term goes to global memory for the pair -- a plain 64-bit store when the pair is the whole PUB (nobody
+// else adds to those tallies; they were zeroed by the launch), a RED otherwise.  Measured on cfg4 (two tiles per PUB):
+// the REDs of the one-tile flush cost 5.5 % of K1 (scripts/micro/k1_compute_only.py).
+template <int T>
+QCUT_DEV void qcut_flush_gather(const uint32_t* acc, int lane, uint32_t* mine) {
+  constexpr int NACC = (T + 3) / 4;
+  const int field = lane & 3;
+  const bool odd_field = field & 1;
+  const uint32_t shift = (field & 2) ? 16u : 0u;
+  const int owner = lane >> 2;
+#pragma unroll
+  for (int r = 0; r < NACC; ++r) {
+    const uint32_t ev = __reduce_add_sync(0xffffffffu, acc[r] & 0x00FF00FFu);
+    const uint32_t od = __reduce_add_sync(0xffffffffu, (acc[r] >> 8) & 0x00FF00FFu);
+    const uint32_t val = ((odd_field ? od : ev) >> shift) & 0xFFFFu;
+    if ((r & 7) == owner) mine[r >> 3] += val;
+  }
+}
+template <int T>
+QCUT_DEV void qcut_flush_commit(const uint32_t* mine, long long ns, int lane, unsigned long long* __restrict__ tally, bool whole_pub) {
+  constexpr int NACC = (T + 3) / 4;
+  const int field = lane & 3;
+  const int owner = lane >> 2;
+#pragma unroll
+  for (int c = 0; c < (NACC + 7) / 8; ++c) {
+    const int r = 8 * c + owner;
+    const int t = field * NACC + r;
+    if (r < NACC && t < T) {
+      const unsigned long long v = (unsigned long long)(ns - 2ll * (long long)mine[c]);
+      if (whole_pub) tally[t] = v;
+      else qcut_red_add(tally + t, v);
+    }
+  }
+}
 // The same flush for a network whose number of terms is only known at run time (kernels that serve many small
 // groups, Net::run switches on the group's variant): T terms in nacc = ceil(T / 4) <= MAXNACC <= 8 packed registers,
 // so every lane owns at most one (register, field).

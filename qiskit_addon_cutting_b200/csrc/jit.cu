@@ -1015,6 +1015,8 @@ int jit_build(qcut_plan* plan, bool load) {
       for (int g : jk.variants) gds.push_back(&plan->groups[g]);
       jk.threads = 256;
       jk.min_blocks = 2;
+      if (const char* env_mb = std::getenv("QCUT_JIT_SWITCH_MINBLOCKS"))  // experiments
+        if (*env_mb && std::atoi(env_mb) >= 1 && std::atoi(env_mb) <= 8) jk.min_blocks = std::atoi(env_mb);
       jk.nb_obs = (int)gds.front()->nb_obs;
       // these kernels wait on memory (a few terms per group): staged stream unless switched off
       const char* env_as = std::getenv("QCUT_JIT_AUTO_STAGED");

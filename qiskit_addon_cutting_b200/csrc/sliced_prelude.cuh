@@ -212,11 +212,29 @@ struct QcutGeo {
   static const int QRAW = (NB == 1) ? 32 : (NB == 2) ? 16 : 8;        // raw qpd words per lane per step
 };
 
-// Shot (relative to the step) held by row j, sub-shot u of this lane.
+// Row register of the word that the load geometry above calls row j.  For 1- and 2-byte rows the qpd bytes are as many
+// as (half as many as) the observable bytes, and folding them byte by byte cost as much as the transposition itself
+// (ncu on the molecular workload's kernels after the switch kernels: ALU pipe 60 %, the top stalls `wait` and
+// `math_pipe_throttle`).  The qpd parity planes of these widths come out of a fold-and-pack network instead (fold the
+// high half of every field onto the low half, pack two words into one, three times: qcut_qpd_planes), whose output bits
+// are in bit-reversed row order -- so the observable rows are simply NAMED in that order when they are loaded (row
+// order is arbitrary as long as planes and qpd plane agree; tallies are order independent).  Involutions.
 template <int NB>
-QCUT_DEV int qcut_shot_of(int j, int u, int lane) {
+QCUT_DEV constexpr int qcut_row_reg(int j) {
+  if constexpr (NB == 2)  // j = (p, s3, s2, s1, b1) -> (p, b1, s1, s2, s3)
+    return (j & 16) | ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
+  else if constexpr (NB == 1)  // j = (p1 p0, s3, s2, s1) -> (p1 p0, s1, s2, s3)
+    return (j & 24) | ((j & 1) << 2) | (j & 2) | ((j & 4) >> 2);
+  else
+    return j;
+}
+
+// Shot (relative to the step) held by row register j, sub-shot u of this lane.
+template <int NB>
+QCUT_DEV int qcut_shot_of(int jr, int u, int lane) {
   typedef QcutGeo<NB> G;
-  if constexpr (G::GROUPED) return ((j >> 4) * 32 + lane) * 16 + (j & 15);
+  if constexpr (G::GROUPED) return ((jr >> 4) * 32 + lane) * 16 + (jr & 15);
+  const int j = qcut_row_reg<NB>(jr);
   const int k = j / G::RPC, e = j % G::RPC;
   return (k * 32 + lane) * G::SPC + e * G::BATCHES + u;
 }
@@ -280,7 +298,8 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
         a[0][2 * k] = v.x; a[1][2 * k] = v.y;
         a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
       } else {
-        a[0][4 * k] = v.x; a[0][4 * k + 1] = v.y; a[0][4 * k + 2] = v.z; a[0][4 * k + 3] = v.w;
+        a[0][qcut_row_reg<NB>(4 * k)] = v.x; a[0][qcut_row_reg<NB>(4 * k + 1)] = v.y;
+        a[0][qcut_row_reg<NB>(4 * k + 2)] = v.z; a[0][qcut_row_reg<NB>(4 * k + 3)] = v.w;
       }
     }
   }
@@ -340,15 +359,34 @@ QCUT_DEV void qcut_qpd_loads(const Src src, int n, int lane, uint32_t* qraw) {
 template <int NB>
 QCUT_DEV void qcut_qpd_planes(uint32_t* qraw, uint32_t* qp) {
   typedef QcutGeo<NB> G;
-  if constexpr (NB == 1) {
-    // Same geometry as the observable rows: transpose the qpd block too, XOR its 8 planes per batch.
-    qcut_transpose32(qraw);
+  if constexpr (NB == 1 || NB == 2) {
+    // Fold-and-pack: after `v ^= v >> 4` the low nibble of every byte carries the byte's parity information, so two words
+    // share one (low nibbles of the first, low nibbles of the second moved up); the same with 2-bit and 1-bit fields.
+    // QRAW words -> QRAW / 8 words whose byte b holds, at bit 4 s1 + 2 s2 + s3, the parity of byte b of raw word
+    // 8 p + 4 s3 + 2 s2 + s1.  86 instructions for 16 words instead of ~250 byte by byte.
+    constexpr int N = G::QRAW;
 #pragma unroll
-    for (int u = 0; u < G::BATCHES; ++u) {
-      uint32_t x = 0;
+    for (int i = 0; i < N; ++i) qraw[i] ^= qcut_shr<4>(qraw[i]);
 #pragma unroll
-      for (int b = 0; b < G::PLANES; ++b) x ^= qraw[u * G::PLANES + b];
-      qp[u] = x;
+    for (int i = 0; i < N / 2; ++i) qraw[i] = qcut_sel<0x0F0F0F0Fu>(qraw[2 * i], qraw[2 * i + 1] << 4);
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) qraw[i] ^= qcut_shr<2>(qraw[i]);
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) qraw[i] = qcut_sel<0x33333333u>(qraw[2 * i], qraw[2 * i + 1] << 2);
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) qraw[i] ^= qcut_shr<1>(qraw[i]);
+#pragma unroll
+    for (int i = 0; i < N / 8; ++i) qraw[i] = qcut_sel<0x55555555u>(qraw[2 * i], qraw[2 * i + 1] << 1);
+    if constexpr (NB == 2) {  // bytes (0, 2) of a raw word belong to batch 0, (1, 3) to batch 1
+      qp[0] = __byte_perm(qraw[0], qraw[1], 0x6420);
+      qp[1] = __byte_perm(qraw[0], qraw[1], 0x7531);
+    } else {  // byte u of a raw word belongs to batch u
+      const uint32_t lo02 = __byte_perm(qraw[0], qraw[1], 0x6240), lo13 = __byte_perm(qraw[0], qraw[1], 0x7351);
+      const uint32_t hi02 = __byte_perm(qraw[2], qraw[3], 0x6240), hi13 = __byte_perm(qraw[2], qraw[3], 0x7351);
+      qp[0] = __byte_perm(lo02, hi02, 0x5410);
+      qp[2] = __byte_perm(lo02, hi02, 0x7632);
+      qp[1] = __byte_perm(lo13, hi13, 0x5410);
+      qp[3] = __byte_perm(lo13, hi13, 0x7632);
     }
   } else {
     // Fold each byte to its parity, then gather the parity bits of four bytes with one multiply

@@ -225,16 +225,26 @@ QCUT_DEV constexpr int qcut_row_reg(int j) {
     return (j & 16) | ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
   else if constexpr (NB == 1)  // j = (p1 p0, s3, s2, s1) -> (p1 p0, s1, s2, s3)
     return (j & 24) | ((j & 1) << 2) | (j & 2) | ((j & 4) >> 2);
+  else if constexpr (NB >= 3 && NB <= 7)  // qpd word i = j / 4 = (s3 s2 s1), byte b = j % 4 -> (b, s1, s2, s3)
+    return ((j & 3) << 3) | (j & 4) | ((j & 8) >> 2) | ((j & 16) >> 4);
   else
     return j;
+}
+// ... and back (rows 3..7 bytes wide: not an involution)
+template <int NB>
+QCUT_DEV constexpr int qcut_reg_row(int r) {
+  if constexpr (NB >= 3 && NB <= 7)
+    return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | (r >> 3);
+  else
+    return qcut_row_reg<NB>(r);
 }
 
 // Shot (relative to the step) held by row register j, sub-shot u of this lane.
 template <int NB>
 QCUT_DEV int qcut_shot_of(int jr, int u, int lane) {
   typedef QcutGeo<NB> G;
-  if constexpr (G::GROUPED) return ((jr >> 4) * 32 + lane) * 16 + (jr & 15);
-  const int j = qcut_row_reg<NB>(jr);
+  const int j = qcut_reg_row<NB>(jr);
+  if constexpr (G::GROUPED) return ((j >> 4) * 32 + lane) * 16 + (j & 15);
   const int k = j / G::RPC, e = j % G::RPC;
   return (k * 32 + lane) * G::SPC + e * G::BATCHES + u;
 }
@@ -286,7 +296,7 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
         for (int blk = 0; blk < G::BLOCKS; ++blk) {
           const int o = r * NB + 4 * blk;
           const int wi = o >> 2, sh = o & 3;
-          a[blk][16 * g + r] = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], 0x3210 + 0x1111 * sh);
+          a[blk][qcut_row_reg<NB>(16 * g + r)] = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], 0x3210 + 0x1111 * sh);
         }
     }
   } else {
@@ -388,6 +398,19 @@ QCUT_DEV void qcut_qpd_planes(uint32_t* qraw, uint32_t* qp) {
       qp[1] = __byte_perm(lo13, hi13, 0x5410);
       qp[3] = __byte_perm(lo13, hi13, 0x7632);
     }
+  } else if constexpr (NB >= 3 && NB <= 7) {
+    // eight raw words (word i = bytes of rows 4 i .. 4 i + 3) -> one word, same network: 42 instructions instead of 88
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qraw[i] ^= qcut_shr<4>(qraw[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qraw[i] = qcut_sel<0x0F0F0F0Fu>(qraw[2 * i], qraw[2 * i + 1] << 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qraw[i] ^= qcut_shr<2>(qraw[i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) qraw[i] = qcut_sel<0x33333333u>(qraw[2 * i], qraw[2 * i + 1] << 2);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) qraw[i] ^= qcut_shr<1>(qraw[i]);
+    qp[0] = qcut_sel<0x55555555u>(qraw[0], qraw[1] << 1);
   } else {
     // Fold each byte to its parity, then gather the parity bits of four bytes with one multiply
     // (no carries: all partial products hit distinct bits).

@@ -219,13 +219,20 @@ struct QcutGeo {
 // high half of every field onto the low half, pack two words into one, three times: qcut_qpd_planes), whose output bits
 // are in bit-reversed row order -- so the observable rows are simply NAMED in that order when they are loaded (row
 // order is arbitrary as long as planes and qpd plane agree; tallies are order independent).  Involutions.
+// (8-byte rows take part only in kernels whose generator defines QCUT_FOLD8: the experimental engines for that width
+//  load their rows with code of their own)
+#ifdef QCUT_FOLD8
+#define QCUT_FOLD_NB(NB) ((NB) >= 3 && (NB) <= 8)
+#else
+#define QCUT_FOLD_NB(NB) ((NB) >= 3 && (NB) <= 7)
+#endif
 template <int NB>
 QCUT_DEV constexpr int qcut_row_reg(int j) {
   if constexpr (NB == 2)  // j = (p, s3, s2, s1, b1) -> (p, b1, s1, s2, s3)
     return (j & 16) | ((j & 1) << 3) | ((j & 2) << 1) | ((j & 4) >> 1) | ((j & 8) >> 3);
   else if constexpr (NB == 1)  // j = (p1 p0, s3, s2, s1) -> (p1 p0, s1, s2, s3)
     return (j & 24) | ((j & 1) << 2) | (j & 2) | ((j & 4) >> 2);
-  else if constexpr (NB >= 3 && NB <= 7)  // qpd word i = j / 4 = (s3 s2 s1), byte b = j % 4 -> (b, s1, s2, s3)
+  else if constexpr (QCUT_FOLD_NB(NB))  // qpd word i = j / 4 = (s3 s2 s1), byte b = j % 4 -> (b, s1, s2, s3)
     return ((j & 3) << 3) | (j & 4) | ((j & 8) >> 2) | ((j & 16) >> 4);
   else
     return j;
@@ -233,7 +240,7 @@ QCUT_DEV constexpr int qcut_row_reg(int j) {
 // ... and back (rows 3..7 bytes wide: not an involution)
 template <int NB>
 QCUT_DEV constexpr int qcut_reg_row(int r) {
-  if constexpr (NB >= 3 && NB <= 7)
+  if constexpr (QCUT_FOLD_NB(NB))
     return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | (r >> 3);
   else
     return qcut_row_reg<NB>(r);
@@ -305,8 +312,8 @@ QCUT_DEV void qcut_step_loads(const Src src, int n, int lane, uint32_t (*a)[32])
       qcut_u4 v = {0u, 0u, 0u, 0u};
       if (FULL || (k * 32 + lane) * G::SPC < n) v = src.obs16(lane * 16 + k * 512);
       if constexpr (NB == 8) {
-        a[0][2 * k] = v.x; a[1][2 * k] = v.y;
-        a[0][2 * k + 1] = v.z; a[1][2 * k + 1] = v.w;
+        a[0][qcut_row_reg<NB>(2 * k)] = v.x; a[1][qcut_row_reg<NB>(2 * k)] = v.y;
+        a[0][qcut_row_reg<NB>(2 * k + 1)] = v.z; a[1][qcut_row_reg<NB>(2 * k + 1)] = v.w;
       } else {
         a[0][qcut_row_reg<NB>(4 * k)] = v.x; a[0][qcut_row_reg<NB>(4 * k + 1)] = v.y;
         a[0][qcut_row_reg<NB>(4 * k + 2)] = v.z; a[0][qcut_row_reg<NB>(4 * k + 3)] = v.w;
@@ -398,7 +405,7 @@ QCUT_DEV void qcut_qpd_planes(uint32_t* qraw, uint32_t* qp) {
       qp[1] = __byte_perm(lo13, hi13, 0x5410);
       qp[3] = __byte_perm(lo13, hi13, 0x7632);
     }
-  } else if constexpr (NB >= 3 && NB <= 7) {
+  } else if constexpr (QCUT_FOLD_NB(NB)) {
     // eight raw words (word i = bytes of rows 4 i .. 4 i + 3) -> one word, same network: 42 instructions instead of 88
 #pragma unroll
     for (int i = 0; i < 8; ++i) qraw[i] ^= qcut_shr<4>(qraw[i]);

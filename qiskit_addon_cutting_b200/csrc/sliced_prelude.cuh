@@ -1167,6 +1167,13 @@ QCUT_DEV void qcut_red_add(unsigned long long* p, unsigned long long v) {
 // register is widened to two pairs of 16-bit fields (the warp sum is <= 4096) and summed with two
 // REDUX; lane l = 4 * (r % 8) + f keeps the total of (register r, field f) for r = l/4, l/4 + 8, ...,
 // and the warp finishes with ceil(NACC / 8) 64-bit reductions to global memory.
+// warp sum of a 32-bit value (plain REDUX: the lanes of a warp are converged here by construction)
+QCUT_DEV uint32_t qcut_redux_add(uint32_t v) {
+  uint32_t r;
+  asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
+}
+
 template <int T>
 QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long long* __restrict__ tally) {
   constexpr int NACC = (T + 3) / 4;
@@ -1174,21 +1181,24 @@ QCUT_DEV void qcut_flush(const uint32_t* acc, int ns, int lane, unsigned long lo
 #pragma unroll
   for (int c = 0; c < (NACC + 7) / 8; ++c) mine[c] = 0;
   const int field = lane & 3;
-  const bool odd_field = field & 1;
-  const uint32_t shift = (field & 2) ? 16u : 0u;
   const int owner = lane >> 2;  // this lane owns registers r with r % 8 == owner
+  // this lane's field is one 16-bit half of the pair (ev, od): field 0 -> ev low, 1 -> od low, 2 -> ev high, 3 -> od high;
+  // one PRMT with a per-lane selector takes it out (upper half: don't care, masked once at the end)
+  const uint32_t first = ((field & 1) ? 4u : 0u) + ((field & 2) ? 2u : 0u);
+  const uint32_t pick = ((first + 1u) << 4) | first;
 #pragma unroll
   for (int r = 0; r < NACC; ++r) {
-    const uint32_t ev = __reduce_add_sync(0xffffffffu, acc[r] & 0x00FF00FFu);         // fields 0, 2
-    const uint32_t od = __reduce_add_sync(0xffffffffu, (acc[r] >> 8) & 0x00FF00FFu);  // fields 1, 3
-    const uint32_t val = ((odd_field ? od : ev) >> shift) & 0xFFFFu;
+    const uint32_t ev = qcut_redux_add(acc[r] & 0x00FF00FFu);                  // fields 0, 2
+    const uint32_t od = qcut_redux_add(__byte_perm(acc[r], 0u, 0x4341));      // fields 1, 3: bytes (1, -, 3, -)
+    const uint32_t val = __byte_perm(ev, od, pick);
     if ((r & 7) == owner) mine[r >> 3] = val;
   }
 #pragma unroll
   for (int c = 0; c < (NACC + 7) / 8; ++c) {
     const int r = 8 * c + owner;
     const int t = field * NACC + r;
-    if (r < NACC && t < T) qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)mine[c]));
+    if (r < NACC && t < T)
+      qcut_red_add(tally + t, (unsigned long long)((long long)ns - 2ll * (long long)(mine[c] & 0xFFFFu)));
   }
 }
 // The flush in two halves, for kernels in which a warp takes the tiles of a PUB two at a time (8192 shots): the warp

@@ -626,6 +626,8 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
           "#endif\n";
     return os.str();
   }
+  const char* env_pair = std::getenv("QCUT_JIT_PAIR");
+  const bool pair = plain && !sacc && !pipe && nb <= 8 && env_pair && *env_pair && std::atoi(env_pair) != 0;
   os << "#ifndef QCUT_HOST_EMU\n";
   os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n";
   if (split) {
@@ -687,6 +689,58 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
           "  qcut_warp_pipe<Terms>(data, pubs, tiles, n_tiles, (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),\n"
           "                        (int64_t)gridDim.x * (blockDim.x >> 5), tallies, lane);\n"
           "}\n";
+  } else if (pair) {
+    // Experiment (QCUT_JIT_PAIR=1, off by default): a warp takes the tile list two entries at a time; two consecutive
+    // tiles of one PUB share one update of the tallies (qcut_flush_gather / qcut_flush_commit), a plain store when
+    // they are the whole PUB.  Bit-exact, but the five registers that carry the gathered sums across a tile push the
+    // step loop over the 128-register cliff (STACK 64 -> 96): cfg4 0.764 -> 0.691 of the copy peak, cfg3 dense
+    // 0.350 -> 0.320.
+    os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
+          "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
+          "                  unsigned long long* __restrict__ tallies) {\n"
+          "  const int lane = threadIdx.x & 31;\n"
+          "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
+          "  for (int64_t tile = 2 * ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); tile < n_tiles;\n"
+          "       tile += 2 * n_warps) {\n"
+          "    uint32_t mine[(Terms::NACC + 7) / 8];\n"
+          "#pragma unroll\n"
+          "    for (int c = 0; c < (Terms::NACC + 7) / 8; ++c) mine[c] = 0;\n"
+          "    QcutTile te = tiles[tile];\n"
+          "    QcutPub pub = pubs[te.pub];\n"
+          "    long long ns_sum = 0;\n"
+          "    uint32_t first_tile = te.tile_in_pub;\n"
+          "#pragma unroll 1\n"
+          "    for (int h = 0; h < 2 && tile + h < n_tiles; ++h) {\n"
+          "      if (h == 1) {\n"
+          "        const QcutTile te2 = tiles[tile + 1];\n"
+          "        if (te2.pub != te.pub) {  // the second entry belongs to another PUB: finish the first on its own\n"
+          "          qcut_flush_commit<Terms::T>(mine, ns_sum, lane, tallies + pub.tally_offset,\n"
+          "                                      first_tile == 0 && ns_sum == (long long)pub.shots);\n"
+          "#pragma unroll\n"
+          "          for (int c = 0; c < (Terms::NACC + 7) / 8; ++c) mine[c] = 0;\n"
+          "          ns_sum = 0;\n"
+          "          pub = pubs[te2.pub];\n"
+          "          first_tile = te2.tile_in_pub;\n"
+          "        }\n"
+          "        te = te2;\n"
+          "      }\n"
+          "      const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
+          "      const int64_t left = (int64_t)pub.shots - shot0;\n"
+          "      const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
+          "      const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
+          "      const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
+          "      uint32_t acc[Terms::NACC];\n";
+    if (il)
+      os << "      qcut_lane_tile_il<Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n";
+    else
+      os << "      qcut_lane_tile<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n";
+    os << "      qcut_flush_gather<Terms::T>(acc, lane, mine);\n"
+          "      ns_sum += ns;\n"
+          "    }\n"
+          "    qcut_flush_commit<Terms::T>(mine, ns_sum, lane, tallies + pub.tally_offset,\n"
+          "                                first_tile == 0 && ns_sum == (long long)pub.shots);\n"
+          "  }\n"
+          "}\n";
   } else if (staged) {
     // Bulk-copy staged stream: one staging buffer + one mbarrier per warp in dynamic shared memory.
     os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
@@ -720,66 +774,6 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
             "    const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
             "    const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
             "    uint32_t acc[Terms::NACC];\n";
-      const char* env_pair = std::getenv("QCUT_JIT_PAIR");
-      if (prefetch == 0 && env_pair && *env_pair && std::atoi(env_pair) != 0) {
-        // Experiment (QCUT_JIT_PAIR=1, off by default): a warp takes the tile list two entries at a time; two consecutive
-        // tiles of one PUB share one update of the tallies (qcut_flush_gather / qcut_flush_commit), a plain store when
-        // they are the whole PUB.  Bit-exact, but the five registers that carry the gathered sums across a tile push the
-        // step loop over the 128-register cliff (STACK 64 -> 96): cfg4 0.764 -> 0.691 of the copy peak, cfg3 dense
-        // 0.350 -> 0.320.
-        os.str(std::string());  // (restart the kernel text: different loop)
-        os.clear();
-        os << "#define QCUT_SACC_STRIDE " << 16 * threads << "\n" << kPrelude << "\n" << terms.str();
-        os << "#ifndef QCUT_HOST_EMU\n";
-        os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n";
-        os << "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
-              "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
-              "                  unsigned long long* __restrict__ tallies) {\n"
-              "  const int lane = threadIdx.x & 31;\n"
-              "  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);\n"
-              "  for (int64_t tile = 2 * ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); tile < n_tiles;\n"
-              "       tile += 2 * n_warps) {\n"
-              "    uint32_t mine[(Terms::NACC + 7) / 8];\n"
-              "#pragma unroll\n"
-              "    for (int c = 0; c < (Terms::NACC + 7) / 8; ++c) mine[c] = 0;\n"
-              "    QcutTile te = tiles[tile];\n"
-              "    QcutPub pub = pubs[te.pub];\n"
-              "    long long ns_sum = 0;\n"
-              "    uint32_t first_tile = te.tile_in_pub;\n"
-              "#pragma unroll 1\n"
-              "    for (int h = 0; h < 2 && tile + h < n_tiles; ++h) {\n"
-              "      if (h == 1) {\n"
-              "        const QcutTile te2 = tiles[tile + 1];\n"
-              "        if (te2.pub != te.pub) {  // the second entry belongs to another PUB: finish the first on its own\n"
-              "          qcut_flush_commit<Terms::T>(mine, ns_sum, lane, tallies + pub.tally_offset,\n"
-              "                                      first_tile == 0 && ns_sum == (long long)pub.shots);\n"
-              "#pragma unroll\n"
-              "          for (int c = 0; c < (Terms::NACC + 7) / 8; ++c) mine[c] = 0;\n"
-              "          ns_sum = 0;\n"
-              "          pub = pubs[te2.pub];\n"
-              "          first_tile = te2.tile_in_pub;\n"
-              "        }\n"
-              "        te = te2;\n"
-              "      }\n"
-              "      const int64_t shot0 = (int64_t)te.tile_in_pub * QCUT_TILE_SHOTS;\n"
-              "      const int64_t left = (int64_t)pub.shots - shot0;\n"
-              "      const int ns = left < QCUT_TILE_SHOTS ? (int)left : QCUT_TILE_SHOTS;\n"
-              "      const uint8_t* __restrict__ obs = data + pub.obs_offset + (uint64_t)shot0 * Terms::NB;\n"
-              "      const uint8_t* __restrict__ qpd = data + pub.qpd_offset + (uint64_t)shot0 * pub.nb_qpd;\n"
-              "      uint32_t acc[Terms::NACC];\n";
-        if (il)
-          os << "      qcut_lane_tile_il<Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n";
-        else
-          os << "      qcut_lane_tile<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc);\n";
-        os << "      qcut_flush_gather<Terms::T>(acc, lane, mine);\n"
-              "      ns_sum += ns;\n"
-              "    }\n"
-              "    qcut_flush_commit<Terms::T>(mine, ns_sum, lane, tallies + pub.tally_offset,\n"
-              "                                first_tile == 0 && ns_sum == (long long)pub.shots);\n"
-              "  }\n"
-              "}\n";
-        goto emu_entry;
-      }
       if (prefetch == 1)
         os << "    qcut_lane_tile_pf<Terms::NB, Terms>(obs, qpd, (int)pub.nb_qpd, ns, lane, acc, obs, qpd, 1, 0);\n";
       else if (il)
@@ -826,7 +820,6 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
           "}\n";
     }
   }
-emu_entry:
   os << "#else  // host emulation entry: one lane of one tile, unpacked odd counts\n";
   os << "extern \"C\" int qcut_emu_lane_tile(const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
         "                                  uint32_t* odd_out) {\n"

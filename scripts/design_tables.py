@@ -61,9 +61,9 @@ def cold_table(d):
 def ncu_table():
     import re
 
-    names = [("k1_cfg4", "K1 specialised, cfg4 (8+1 B rows, 134 terms)"), ("k1_cfg5", "K1 cfg5: 8 single-group + 5 multi-group kernels (scale 0.5)"),
-             ("k1_cfg3_local", "K1 cfg3 local (9 kernels, 1-7 B rows)"), ("k1_cfg3_dense", "K1 cfg3 dense (100 terms x 32 planes)"),
-             ("k1_wide", "K1 wide rows (16 B, 271 terms)"), ("k1_rt", "K1 run-time masks (ahead of time), cfg4 rows"),
+    names = [("k1_cfg4", "K1 specialised, cfg4 (8+1 B rows, 134 terms)"), ("k1_cfg5", "K1 cfg5: its 4 switch kernels, staged stream (scale 0.5)"),
+             ("k1_cfg3_local", "K1 cfg3 local (2 mixed-width kernels, 1-7 B rows)"), ("k1_cfg3_dense", "K1 cfg3 dense (100 terms x 32 planes)"),
+             ("k1_wide_slab", "K1 16-byte rows in 8-byte slabs (271 terms)"), ("k1_wide", "K1 wide rows, shared-memory engine (16 B, 271 terms)"), ("k1_rt", "K1 run-time masks (ahead of time), cfg4 rows"),
              ("k1_generic", "K1 generic (AND/POPC per shot), cfg4 rows"), ("k2_stream", "K2 stream (cfg4, 97 000 tuples)"),
              ("literal", "K1-literal (reference rounding), cfg4 rows")]
     out = ["| kernel (`profiles/r02_<name>_ncu_summary.txt`) | launches | time | DRAM % of peak | issue slots % | ALU / XU / FMA pipe % | registers | warps per scheduler | global-load sectors per request | requested / ideal L2 sectors | L2->SM sectors per DRAM sector | top stalls |",

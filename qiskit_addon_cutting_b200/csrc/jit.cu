@@ -514,6 +514,7 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   // Register budget: 32 per live block + packed counters + ~28 of addressing / temporaries.
   const int budget = ((nb > 4 && !split) ? 64 : 32) + (int)((T + 3) / 4) + 28;
   int min_blocks = budget > 128 ? 1 : 2;
+  if (slab || sacc) min_blocks = 2;  // packed counters in shared memory: 64 planes + temporaries fit 128 registers
   if (split && threads * 3 * (budget + 8) <= 65536) min_blocks = 3;  // one block at a time: three CTAs share an SM
   if (!split && nb <= 8) {
     // experiment knob (measured slower, see the multi-group kernels in jit_build): more CTAs per SM for small budgets
@@ -539,7 +540,11 @@ std::string generate_sliced_source(const qcut_group_desc& gd, const uint8_t* mas
   }
   if (slab) {
     const char* env_pf = std::getenv("QCUT_JIT_SLAB_PREFETCH");
-    if (!(env_pf && *env_pf && std::atoi(env_pf) == 0)) os << "#define QCUT_SLAB_PREFETCH 1\n";
+    // measured on 16-byte rows at 2 CTAs per SM: plain 0.557 of the copy peak, L2 prefetch of the next step 0.594, L2
+    // eviction hints (evict-last until the last slab has read a sector) 0.621, both 0.617 -> hints on, prefetch off
+    if (env_pf && *env_pf && std::atoi(env_pf) != 0) os << "#define QCUT_SLAB_PREFETCH 1\n";
+    const char* env_hint = std::getenv("QCUT_JIT_SLAB_L2_HINTS");
+    if (!(env_hint && *env_hint && std::atoi(env_hint) == 0)) os << "#define QCUT_SLAB_L2_HINTS 1\n";
   }
   os << kPrelude << "\n";
   os << terms.str();

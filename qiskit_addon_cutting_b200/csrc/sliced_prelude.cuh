@@ -1042,13 +1042,38 @@ QCUT_DEV void qcut_ld8(const uint8_t* p, uint32_t& lo, uint32_t& hi) {
 QCUT_DEV void qcut_ld8(const uint8_t* p, uint32_t& lo, uint32_t& hi) { memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4); }
 #endif
 
+// Every 32-byte sector of a step is read once per slab.  ncu on 16-byte rows: 1.48 x the algorithmic bytes come from
+// DRAM, i.e. about half of the second slab's sectors have left L2 again by the time they are wanted (16 warps per SM x
+// 17 KB per step, two steps with the prefetch).  So the slabs say what they know: all but the last slab load with an
+// L2 evict-last policy, the last one with evict-first (QCUT_SLAB_L2_HINTS, set by the generator).
+#if !defined(QCUT_HOST_EMU) && defined(QCUT_SLAB_L2_HINTS)
+QCUT_DEV uint64_t qcut_l2_policy(bool last_use) {
+  uint64_t pol;
+  if (last_use) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+QCUT_DEV void qcut_ld8_hint(const uint8_t* p, uint64_t pol, uint32_t& lo, uint32_t& hi) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(lo), "=r"(hi) : "l"(p), "l"(pol));
+}
+#endif
+
 template <int NB, bool FULL>
 QCUT_DEV void qcut_slab_loads(const uint8_t* __restrict__ obs_s, int slab, int n, int lane, uint32_t (*a)[32]) {
+#if !defined(QCUT_HOST_EMU) && defined(QCUT_SLAB_L2_HINTS)
+  const uint64_t pol = qcut_l2_policy(slab + 1 == NB / 8);
+#endif
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
     a[0][k] = 0;
     a[1][k] = 0;
-    if (FULL || 32 * k + lane < n) qcut_ld8(obs_s + (uint64_t)(32 * k + lane) * NB + 8 * slab, a[0][k], a[1][k]);
+    if (FULL || 32 * k + lane < n) {
+#if !defined(QCUT_HOST_EMU) && defined(QCUT_SLAB_L2_HINTS)
+      qcut_ld8_hint(obs_s + (uint64_t)(32 * k + lane) * NB + 8 * slab, pol, a[0][k], a[1][k]);
+#else
+      qcut_ld8(obs_s + (uint64_t)(32 * k + lane) * NB + 8 * slab, a[0][k], a[1][k]);
+#endif
+    }
   }
 }
 

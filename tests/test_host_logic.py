@@ -113,3 +113,49 @@ def test_compiled_kernels_are_cached_on_disk(lib, tmp_path, monkeypatch):
     before = len(list(cache.glob("*")))
     assert L.plan_compile_check(groups, masks) == (n, size)
     assert len(list(cache.glob("*"))) == before
+
+
+def _sets(rng, n_sets, n_terms, nb):
+    """n_sets distinct groups of n_terms random masks on nb-byte rows: (group records, mask bytes) for plan creation."""
+    from qiskit_addon_cutting_b200 import _lib as L
+
+    groups = np.zeros(n_sets, dtype=L.GROUP_DTYPE)
+    chunks, offset = [], 0
+    for g in range(n_sets):
+        rows = rng.integers(0, 256, size=(n_terms, nb), dtype=np.uint8)
+        rows[:, 0] |= 1  # no all-zero row, sets differ with overwhelming probability
+        groups[g] = (n_terms, nb, offset, 0)
+        chunks.append(rows.reshape(-1))
+        offset += rows.size
+    return groups, np.concatenate(chunks)
+
+
+def _merge(parts):
+    from qiskit_addon_cutting_b200 import _lib as L
+
+    groups = np.concatenate([g for g, _ in parts]).astype(L.GROUP_DTYPE)
+    masks, offset, first = [], 0, 0
+    for g, m in parts:
+        groups["mask_offset"][first:first + len(g)] = g["mask_offset"] + offset
+        masks.append(m)
+        offset += m.size
+        first += len(g)
+    return groups, np.concatenate(masks)
+
+
+def test_which_groups_share_a_kernel(lib, tmp_path, monkeypatch):
+    """Kernel assignment of a plan (api.cu: assign_jit_kernels), read off the number of NVRTC kernels it compiles: groups of
+    more than 32 terms get a kernel each; smaller ones share a switch kernel per row width (64 sets each) when a width has
+    at least 4 sets or is alone, a mixed-width kernel (24 sets each) otherwise."""
+    from qiskit_addon_cutting_b200 import _lib as L
+
+    monkeypatch.setenv("QCUT_CACHE_DIR", str(tmp_path))
+    rng = np.random.default_rng(11)
+    count = lambda parts: L.plan_compile_check(*_merge(parts))[0]  # noqa: E731
+    assert count([_sets(rng, 2, 33, 2)]) == 2                      # two big groups: a kernel each
+    assert count([_sets(rng, 70, 5, 2)]) == 2                      # one width, 70 small sets: 64 + 6 behind switches
+    assert count([_sets(rng, 5, 5, 1), _sets(rng, 6, 7, 2)]) == 2  # two widths with >= 4 sets each: one switch kernel per width
+    assert count([_sets(rng, 2, 5, 1), _sets(rng, 3, 7, 3), _sets(rng, 1, 9, 6)]) == 1  # a handful per width: one mixed kernel
+    assert count([_sets(rng, 1, 40, 8), _sets(rng, 3, 6, 8)]) == 2  # a big group and three small ones of the only small width
+    monkeypatch.setenv("QCUT_JIT_SWITCH", "0")
+    assert count([_sets(rng, 70, 5, 2)]) == 3                      # the older scheme: 24 functions per kernel

@@ -266,6 +266,13 @@ int qcut_compile_source(const char* source, size_t* cubin_bytes, char* cubin_buf
 int qcut_plan_compile_check(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks,
                             size_t mask_bytes, int* n_kernels, size_t* cubin_bytes);
 
+/* The CUDA source of specialised kernel `kernel` (0-based) of the plan these groups would get, and -- when the pointers
+ * are given -- for every group the index of the specialised kernel that serves it (< 0: an ahead-of-time kernel) and
+ * the index of its network inside that kernel.  Returns the length needed including the NUL, 0 if there is no such
+ * kernel.  Host only (runs the kernel assignment and NVRTC like qcut_plan_compile_check). */
+size_t qcut_plan_kernel_source(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks, size_t mask_bytes,
+                               int kernel, char* buf, size_t buf_len, int* kernel_of_group, int* variant_of_group);
+
 #ifdef __cplusplus
 }
 #endif

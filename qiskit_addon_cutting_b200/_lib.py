@@ -111,6 +111,7 @@ SIGNATURES = {
     "qcut_generate_source": (_SZ, [_VP, _INT, _VP, _SZ, _INT, C.c_char_p, _SZ]),
     "qcut_compile_source": (_INT, [C.c_char_p, C.POINTER(_SZ), _VP, _SZ]),
     "qcut_plan_compile_check": (_INT, [_VP, _INT, _VP, _SZ, C.POINTER(_INT), C.POINTER(_SZ)]),
+    "qcut_plan_kernel_source": (_SZ, [_VP, _INT, _VP, _SZ, _INT, C.c_char_p, _SZ, _VP, _VP]),
 }
 
 _lib = None
@@ -195,6 +196,23 @@ def compile_source(source: str) -> bytes:
     buf = C.create_string_buffer(size.value)
     check(lib.qcut_compile_source(src, C.byref(size), buf, size.value), "qcut_compile_source")
     return buf.raw
+
+
+def plan_kernel_source(groups: np.ndarray, masks: np.ndarray, kernel: int) -> tuple[str, np.ndarray, np.ndarray]:
+    """(source of specialised kernel ``kernel`` of the plan these groups would get, kernel index per group, network
+    index per group); the source is empty when there is no such kernel.  Host only."""
+    lib = load()
+    groups = np.ascontiguousarray(groups, dtype=GROUP_DTYPE)
+    masks = np.ascontiguousarray(masks, dtype=np.uint8)
+    mptr = np_ptr(masks) if masks.size else None
+    kernel_of = np.zeros(len(groups), dtype=np.int32)
+    variant_of = np.zeros(len(groups), dtype=np.int32)
+    need = lib.qcut_plan_kernel_source(np_ptr(groups), len(groups), mptr, masks.size, kernel, None, 0, np_ptr(kernel_of), np_ptr(variant_of))
+    if need == 0:
+        return "", kernel_of, variant_of
+    buf = C.create_string_buffer(need)
+    lib.qcut_plan_kernel_source(np_ptr(groups), len(groups), mptr, masks.size, kernel, buf, need, None, None)
+    return buf.value.decode(), kernel_of, variant_of
 
 
 def plan_compile_check(groups: np.ndarray, masks: np.ndarray) -> tuple[int, int]:

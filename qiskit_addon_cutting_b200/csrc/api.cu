@@ -867,6 +867,35 @@ int qcut_stage_h2d(const void* const* h_src, const uint64_t* h_bytes, const uint
   return QCUT_OK;
 }
 
+size_t qcut_plan_kernel_source(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks, size_t mask_bytes,
+                               int kernel, char* buf, size_t buf_len, int* kernel_of_group, int* variant_of_group) {
+  if (!h_groups || n_groups <= 0) return 0;
+  qcut_plan plan;
+  plan.n_groups = n_groups;
+  plan.groups.assign(h_groups, h_groups + n_groups);
+  if (mask_bytes) plan.masks.assign(h_masks, h_masks + mask_bytes);
+  plan.groups_dev.resize((size_t)n_groups);
+  for (int g = 0; g < n_groups; ++g) {
+    if ((size_t)h_groups[g].mask_offset + (size_t)h_groups[g].n_terms * h_groups[g].nb_obs > mask_bytes) return 0;
+    plan.groups_dev[(size_t)g] = GroupDev{};
+    plan.groups_dev[(size_t)g].kernel = sliced_rt_supports(h_groups[g].nb_obs) ? KERNEL_SLICED_RT : KERNEL_GENERIC;
+  }
+  assign_jit_kernels(&plan);
+  if (jit_build(&plan, false) != QCUT_OK) return 0;  // (generates the sources; cubins come from the on-disk cache)
+  for (int g = 0; g < n_groups; ++g) {
+    if (kernel_of_group) kernel_of_group[g] = (int)plan.groups_dev[(size_t)g].kernel - (int)KERNEL_JIT0;  // < 0: ahead-of-time kernel
+    if (variant_of_group) variant_of_group[g] = (int)plan.groups_dev[(size_t)g].variant;
+  }
+  if (kernel < 0 || kernel >= (int)plan.jit.size()) return 0;
+  const std::string& src = plan.jit[(size_t)kernel].source;
+  if (buf && buf_len) {
+    const size_t n = src.size() < buf_len - 1 ? src.size() : buf_len - 1;
+    std::memcpy(buf, src.data(), n);
+    buf[n] = '\0';
+  }
+  return src.size() + 1;
+}
+
 int qcut_plan_compile_check(const qcut_group_desc* h_groups, int n_groups, const uint8_t* h_masks, size_t mask_bytes,
                             int* n_kernels, size_t* cubin_bytes) {
   if (!h_groups || n_groups <= 0) return set_error("qcut_plan_compile_check: no groups"), QCUT_ERR_INVALID;

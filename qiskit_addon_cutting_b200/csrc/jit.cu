@@ -431,8 +431,8 @@ std::string generate_switch_source(const std::vector<const qcut_group_desc*>& gd
     emit_terms(os, "Terms" + std::to_string(v), *gds[v], masks);
     max_nacc = std::max(max_nacc, (gds[v]->n_terms + 3) / 4);
   }
-  os << "#ifndef QCUT_HOST_EMU\n";
-  os << "__constant__ unsigned short qcut_variant_terms[" << gds.size() << "] = {";
+  os << "#ifndef QCUT_HOST_EMU\n__constant__\n#else\nstatic const\n#endif\n";
+  os << "unsigned short qcut_variant_terms[" << gds.size() << "] = {";
   for (size_t v = 0; v < gds.size(); ++v) os << (v ? ", " : "") << gds[v]->n_terms;
   os << "};\n";
   os << "struct Net {\n"
@@ -444,11 +444,14 @@ std::string generate_switch_source(const std::vector<const qcut_group_desc*>& gd
         "    switch (variant) {\n";
   for (size_t v = 0; v < gds.size(); ++v) os << "      case " << v << ": Terms" << v << "::run(P, Q, qp, acc); break;\n";
   os << "      default: break;\n    }\n  }\n"
+        "#ifndef QCUT_HOST_EMU\n"
         "  static QCUT_MDEV void flush(const uint32_t* acc, int ns, int lane, unsigned long long* __restrict__ tally, const int variant) {\n"
         "    const int T = qcut_variant_terms[variant];\n"
         "    qcut_flush_rt<NACC>(acc, T, (T + 3) >> 2, ns, lane, tally);\n"
         "  }\n"
-        "};\n";
+        "#endif\n"
+        "};\n"
+        "#ifndef QCUT_HOST_EMU\n";
   os << "extern \"C\" __global__ void __launch_bounds__(" << threads << ", " << min_blocks << ")\n"
         "qcut_tally_sliced(const uint8_t* __restrict__ data, const QcutPub* __restrict__ pubs,\n"
         "                  const QcutTile* __restrict__ tiles, const int64_t n_tiles,\n"
@@ -482,7 +485,16 @@ std::string generate_switch_source(const std::vector<const qcut_group_desc*>& gd
           "  }\n"
           "}\n";
   }
-  os << "#endif\n";
+  os << "#else  // host emulation entry: one lane of one tile of a group served by network `variant`, unpacked odd counts\n"
+        "extern \"C\" int qcut_emu_lane_tile_variant(int variant, const uint8_t* obs, const uint8_t* qpd, int nbq, int ns, int lane,\n"
+        "                                          uint32_t* odd_out) {\n"
+        "  uint32_t acc[Net::NACC];\n"
+        "  qcut_lane_tile_net<Net::NB, Net>(obs, qpd, nbq, ns, lane, acc, variant);\n"
+        "  const int T = qcut_variant_terms[variant], nacc = (T + 3) >> 2;\n"
+        "  for (int t = 0; t < T; ++t) odd_out[t] = (acc[t % nacc] >> (8 * (t / nacc))) & 0xFFu;\n"
+        "  return T;\n"
+        "}\n"
+        "#endif\n";
   return os.str();
 }
 

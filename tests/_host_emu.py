@@ -45,13 +45,16 @@ def compile_emulator(source: str) -> C.CDLL:
         src.write_text(text)
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-o", str(so), str(src)], check=True)
     lib = C.CDLL(str(so))
-    lib.qcut_emu_lane_tile.restype = C.c_int
-    lib.qcut_emu_lane_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    if hasattr(lib, "qcut_emu_lane_stream"):  # rows of up to 8 bytes only
-        lib.qcut_emu_lane_stream.restype = C.c_int
-        lib.qcut_emu_lane_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]
-    lib.qcut_emu_rt_lane_tile.restype = C.c_int
-    lib.qcut_emu_rt_lane_tile.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    entries = {  # which of them a source exports depends on the kind of kernel
+        "qcut_emu_lane_tile": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p],
+        "qcut_emu_lane_stream": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p],
+        "qcut_emu_rt_lane_tile": [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+        "qcut_emu_lane_tile_variant": [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p],  # switch kernels
+    }
+    for name, argtypes in entries.items():
+        if hasattr(lib, name):
+            getattr(lib, name).restype = C.c_int
+            getattr(lib, name).argtypes = argtypes
     return lib
 
 

@@ -256,3 +256,55 @@ def test_emulated_slab_engine_for_16_24_32_byte_rows(lib, nbits, shots):
         got, covered = _host_emu.emulate_tallies(tables, guarded, "jit")
         assert covered.all() and np.array_equal(got, want)
         del guarded
+
+
+def test_emulated_switch_kernels_of_a_molecular_plan(lib):
+    """Small groups share one kernel per row width, their networks behind a switch on the group's variant index
+    (generate_switch_source).  The same source, compiled for the host, is run lane by lane for every PUB of a
+    molecular-style case (many groups of a few terms on 1- and 2-byte rows, ragged shot counts) and must reproduce the
+    oracle's tallies; the packed-counter layout differs per variant (ceil(T / 4) registers)."""
+    rng = np.random.default_rng(23)
+
+    def strings(n_qubits, count):  # weight-1..3 XYZ strings: qubit-wise commuting groups of a few terms each
+        labels = set()
+        while len(labels) < count:
+            chars = ["I"] * n_qubits
+            for q in rng.choice(n_qubits, size=int(rng.integers(1, 4)), replace=False):
+                chars[q] = "XYZ"[int(rng.integers(3))]
+            labels.add("".join(chars))
+        return sorted(labels)
+
+    # two subsystems: 7 qubits (1-byte rows) and 12 qubits (2-byte rows), the same number of observables each
+    observables = {"A": PauliList(strings(7, 50)), "B": PauliList(strings(12, 50))}
+    results = _cases.make_results(observables, 2, 4500, 2, seed=5)
+    coefficients = [(0.5, WeightType.EXACT), (-0.25, WeightType.EXACT)]
+    tables, data, want = _stage_host(results, coefficients, observables)
+    widths, counts = np.unique(tables.groups["nb_obs"], return_counts=True)
+    assert widths.tolist() == [1, 2] and (counts >= 4).all() and int(tables.groups["n_terms"].max()) <= 32
+    sources, k = {}, 0
+    while True:
+        src, kernel_of, variant_of = _lib.plan_kernel_source(tables.groups, tables.masks, k)
+        if not src:
+            break
+        sources[k] = src
+        k += 1
+    assert sources and all("struct Net" in s and "switch (variant)" in s for s in sources.values()), "switch kernels expected"
+    assert (kernel_of >= 0).all()
+    emus = {kk: _host_emu.compile_emulator(src) for kk, src in sources.items()}
+    got = np.zeros(tables.n_tallies, dtype=np.int64)
+    odd = np.zeros(64, dtype=np.uint32)
+    for pub in tables.pubs:
+        g = int(pub["group"])
+        grp = tables.groups[g]
+        nb, nbq, shots, T = int(grp["nb_obs"]), int(pub["nb_qpd"]), int(pub["shots"]), int(grp["n_terms"])
+        for shot0 in range(0, shots, _lib.TILE_SHOTS):
+            ns = min(_lib.TILE_SHOTS, shots - shot0)
+            total = np.zeros(T, dtype=np.int64)
+            for lane in range(32):
+                n = emus[int(kernel_of[g])].qcut_emu_lane_tile_variant(
+                    int(variant_of[g]), data.ctypes.data + int(pub["obs_offset"]) + shot0 * nb,
+                    data.ctypes.data + int(pub["qpd_offset"]) + shot0 * nbq, nbq, ns, lane, odd.ctypes.data)
+                assert n == T
+                total += odd[:T]
+            got[int(pub["tally_offset"]): int(pub["tally_offset"]) + T] += ns - 2 * total
+    assert np.array_equal(got, want)

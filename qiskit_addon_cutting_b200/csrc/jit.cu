@@ -426,6 +426,7 @@ std::string generate_switch_source(const std::vector<const qcut_group_desc*>& gd
   const uint32_t nb = gds.front()->nb_obs;
   uint32_t max_nacc = 1;
   if (staged) os << "#define QCUT_WITH_VARIANTS 1\n";
+  if (nb == 8) os << "#define QCUT_FOLD8 1\n";  // fold-and-pack qpd plane on 8-byte rows too (rows loaded by qcut_step_loads)
   os << kPrelude << "\n";
   for (size_t v = 0; v < gds.size(); ++v) {
     emit_terms(os, "Terms" + std::to_string(v), *gds[v], masks);

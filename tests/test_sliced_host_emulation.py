@@ -274,13 +274,22 @@ def test_emulated_switch_kernels_of_a_molecular_plan(lib):
             labels.add("".join(chars))
         return sorted(labels)
 
-    # two subsystems: 7 qubits (1-byte rows) and 12 qubits (2-byte rows), the same number of observables each
-    observables = {"A": PauliList(strings(7, 50)), "B": PauliList(strings(12, 50))}
+    def families(n_qubits, n_families, per_family):  # each family: sub-strings of one long XYZ string -> one wide group
+        labels = []
+        for _ in range(n_families):
+            base = ["XYZ"[int(rng.integers(3))] for _ in range(n_qubits)]
+            for _ in range(per_family):
+                keep = rng.random(n_qubits) < 0.7
+                labels.append("".join(c if k else "I" for c, k in zip(base, keep)))
+        return labels
+
+    # three subsystems: 7 qubits (1-byte rows), 12 qubits (2-byte rows), 60 qubits (8-byte rows), 50 observables each
+    observables = {"A": PauliList(strings(7, 50)), "B": PauliList(strings(12, 50)), "C": PauliList(families(60, 5, 10))}
     results = _cases.make_results(observables, 2, 4500, 2, seed=5)
     coefficients = [(0.5, WeightType.EXACT), (-0.25, WeightType.EXACT)]
     tables, data, want = _stage_host(results, coefficients, observables)
     widths, counts = np.unique(tables.groups["nb_obs"], return_counts=True)
-    assert widths.tolist() == [1, 2] and (counts >= 4).all() and int(tables.groups["n_terms"].max()) <= 32
+    assert widths.tolist() == [1, 2, 8] and (counts >= 4).all() and int(tables.groups["n_terms"].max()) <= 32
     sources, k = {}, 0
     while True:
         src, kernel_of, variant_of = _lib.plan_kernel_source(tables.groups, tables.masks, k)
